@@ -1,0 +1,168 @@
+// Warp-resident complex FFT of 1024 points (= real FFT of n_fft = 2048) for sm_100a.
+//
+// Layout: one warp owns one transform.  Lane l holds 32 complex values in registers,
+// element index = 32 * r + l (r = register slot, l = lane).  The transform is the classic
+// 32 x 32 Cooley-Tukey split:
+//     pass 1  32-point FFT over the register index, entirely in registers
+//     twiddle W_1024^(l * k1)   (table in shared memory, conflict-free [k1][l] layout)
+//     32 x 32 transpose through a padded per-warp shared-memory tile (the only exchange)
+//     pass 2  32-point FFT over the register index again
+// Input and output use the same "element = 32 * slot + lane" indexing.  Two flavours:
+//     DIF (analysis):   natural slot order in, bit-reversed slot order out
+//     DIT (synthesis):  bit-reversed slot order in, natural slot order out
+// so a forward DIF transform can hand its registers straight to an inverse DIT transform
+// (the Griffin-Lim iteration does exactly that) and no register permutation is ever
+// executed: every slot index is a compile-time constant after unrolling.
+// No 1/N scaling is applied here -- callers fold it into the synthesis window.
+//
+// The 32-point register FFT is radix-2 with the trivial twiddles (1, -i, (1-i)/sqrt2, ...)
+// special-cased at compile time.  Twiddles are literals rounded from extended precision, so
+// the float32 transform error stays at the ~1e-7 level the Griffin-Lim tolerance budget
+//  assumes; --use_fast_math is never used.
+#pragma once
+#include "simt_compat.h"
+
+namespace sstts {
+
+template <typename T> struct cx_of;
+template <> struct cx_of<float> { typedef float2 type; };
+template <> struct cx_of<double> { typedef double2 type; };
+
+SSTTS_HD constexpr int brev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// cos(2 pi k / 32), k = 0..8, as literals (the rest of the circle by symmetry).
+template <typename T> SSTTS_HD constexpr T cos32_q(int k) {
+  return k == 0 ? T(1.0)
+       : k == 1 ? T(0.9807852804032304491261822)
+       : k == 2 ? T(0.9238795325112867561281832)
+       : k == 3 ? T(0.8314696123025452370787884)
+       : k == 4 ? T(0.7071067811865475244008444)
+       : k == 5 ? T(0.5555702330196022247428308)
+       : k == 6 ? T(0.38268343236508977172846)
+       : k == 7 ? T(0.1950903220161282678482849)
+       : T(0.0);
+}
+// cos / sin of 2 pi k / 32 for k = 0..15.
+template <typename T> SSTTS_HD constexpr T cos32(int k) { return k <= 8 ? cos32_q<T>(k) : -cos32_q<T>(16 - k); }
+template <typename T> SSTTS_HD constexpr T sin32(int k) { return k <= 8 ? cos32_q<T>(8 - k) : cos32_q<T>(k - 8); }
+
+// (dr + i di) * W, W = exp(-/+ 2 pi i idx / 32) (forward: minus, INV: plus), idx in [0, 16).
+template <typename T, bool INV>
+SSTTS_HD void mul_w32(T dr, T di, int idx, T& outr, T& outi) {
+  if (idx == 0) {
+    outr = dr; outi = di;
+  } else if (idx == 8) {
+    if (!INV) { outr = di; outi = -dr; } else { outr = -di; outi = dr; }
+  } else if (idx == 4) {
+    const T h = cos32_q<T>(4);
+    if (!INV) { outr = (dr + di) * h; outi = (di - dr) * h; }
+    else      { outr = (dr - di) * h; outi = (dr + di) * h; }
+  } else if (idx == 12) {
+    const T h = cos32_q<T>(4);
+    if (!INV) { outr = (di - dr) * h; outi = -(dr + di) * h; }
+    else      { outr = -(dr + di) * h; outi = (dr - di) * h; }
+  } else {
+    const T c = cos32<T>(idx), s = sin32<T>(idx);
+    if (!INV) { outr = dr * c + di * s; outi = di * c - dr * s; }
+    else      { outr = dr * c - di * s; outi = di * c + dr * s; }
+  }
+}
+
+// One decimation-in-frequency stage: (a, b) -> (a + b, (a - b) W).
+template <typename T, bool INV, int LEN>
+SSTTS_HD void dif_stage(T (&re)[32], T (&im)[32]) {
+  constexpr int HALF = LEN / 2;
+  constexpr int TSTEP = 32 / LEN;
+#pragma unroll
+  for (int g = 0; g < 32; g += LEN) {
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+      const int i0 = g + j, i1 = g + j + HALF;
+      const T ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+      re[i0] = ar + br;
+      im[i0] = ai + bi;
+      mul_w32<T, INV>(ar - br, ai - bi, j * TSTEP, re[i1], im[i1]);
+    }
+  }
+}
+
+// One decimation-in-time stage: (a, b) -> (a + b W, a - b W).
+template <typename T, bool INV, int LEN>
+SSTTS_HD void dit_stage(T (&re)[32], T (&im)[32]) {
+  constexpr int HALF = LEN / 2;
+  constexpr int TSTEP = 32 / LEN;
+#pragma unroll
+  for (int g = 0; g < 32; g += LEN) {
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+      const int i0 = g + j, i1 = g + j + HALF;
+      T tr, ti;
+      mul_w32<T, INV>(re[i1], im[i1], j * TSTEP, tr, ti);
+      const T ar = re[i0], ai = im[i0];
+      re[i0] = ar + tr;
+      im[i0] = ai + ti;
+      re[i1] = ar - tr;
+      im[i1] = ai - ti;
+    }
+  }
+}
+
+// In-register 32-point FFT.  DIT = false: element k in slot k -> result k in slot brev5(k).
+//                            DIT = true : element k in slot brev5(k) -> result k in slot k.
+template <typename T, bool INV, bool DIT>
+SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
+  if (!DIT) {
+    dif_stage<T, INV, 32>(re, im);
+    dif_stage<T, INV, 16>(re, im);
+    dif_stage<T, INV, 8>(re, im);
+    dif_stage<T, INV, 4>(re, im);
+    dif_stage<T, INV, 2>(re, im);
+  } else {
+    dit_stage<T, INV, 2>(re, im);
+    dit_stage<T, INV, 4>(re, im);
+    dit_stage<T, INV, 8>(re, im);
+    dit_stage<T, INV, 16>(re, im);
+    dit_stage<T, INV, 32>(re, im);
+  }
+}
+
+// Row pitch (in complex elements) of the per-warp transpose tile: 33 keeps both the
+// column-wise stores and the row-wise loads bank-conflict free for 8- and 16-byte elements.
+constexpr int XPITCH = 33;
+constexpr int XTILE_ELEMS = 32 * XPITCH;
+
+// 1024-point complex FFT across one warp; element index = 32 * slot + lane on both sides.
+//   DIT = false: slots natural in, bit-reversed out.   DIT = true: bit-reversed in, natural out.
+// tw[a * 32 + b] = exp(-2 pi i a b / 1024); xt is this warp's private XTILE_ELEMS tile.
+template <typename T, bool INV, bool DIT>
+SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], typename cx_of<T>::type* xt,
+                          const typename cx_of<T>::type* tw, int lane) {
+  typedef typename cx_of<T>::type C;
+  fft32<T, INV, DIT>(re, im);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    const int p = DIT ? k1 : brev5(k1);  // slot holding pass-1 result k1
+    C v;
+    if (k1 == 0) {
+      v.x = re[p]; v.y = im[p];
+    } else {
+      const C w = tw[k1 * 32 + lane];
+      if (!INV) { v.x = re[p] * w.x - im[p] * w.y; v.y = re[p] * w.y + im[p] * w.x; }
+      else      { v.x = re[p] * w.x + im[p] * w.y; v.y = im[p] * w.x - re[p] * w.y; }
+    }
+    xt[k1 * XPITCH + lane] = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) {
+    const C v = xt[lane * XPITCH + n2];
+    const int q = DIT ? brev5(n2) : n2;  // slot expected by pass 2 for element n2
+    re[q] = v.x; im[q] = v.y;
+  }
+  __syncwarp();
+  fft32<T, INV, DIT>(re, im);
+}
+
+}  // namespace sstts

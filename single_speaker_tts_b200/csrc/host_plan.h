@@ -1,0 +1,194 @@
+// Host-side planning shared by the CUDA library (sstts.cu) and the CPU emulator used in tests:
+// tile tables for ragged batches, offset tables, transform tables and the mel filterbank.
+// Plain C++ (no CUDA), so it compiles with g++ as well as nvcc.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "stft_kernels.cuh"
+
+namespace sstts {
+
+// Frames per tile.  Eight frames = one round of an 8-warp CTA; the tail tile of an utterance
+// may hold up to 2 * kMinTile - 1 extra frames, see split_frames().
+constexpr int kTileFrames = 8;
+constexpr int kWarps = 8;
+
+inline int min_tile_frames(int win, int hop) {
+  int v = (win + hop - 1) / hop;  // frames overlapping one sample
+  return v < 4 ? 4 : v;
+}
+
+// Split n_frames into consecutive tiles of `tile` frames; a remainder shorter than `min_tile`
+// borrows frames from its predecessor so every tile of a multi-tile utterance has >= min_tile.
+inline void split_frames(int n_frames, int tile, int min_tile, std::vector<std::pair<int, int> >& out) {
+  out.clear();
+  if (n_frames <= 0) return;
+  if (n_frames <= tile) { out.push_back(std::make_pair(0, n_frames)); return; }
+  int a = 0;
+  while (a < n_frames) {
+    int b = a + tile;
+    if (b >= n_frames) { b = n_frames; }
+    else if (n_frames - b < min_tile) {
+      // leave exactly min_tile frames for the last tile
+      b = n_frames - min_tile;
+      if (b - a < min_tile) b = n_frames;  // cannot split sensibly: merge into one tile
+    }
+    out.push_back(std::make_pair(a, b));
+    a = b;
+  }
+}
+
+struct GLPlanHost {
+  int n_utts = 0, win = 0, hop = 0, span_max = 0, max_tile = 0;
+  std::vector<long long> frame_off, pad_off, sample_off;
+  std::vector<GLTile> tiles;
+  long long total_frames = 0, total_pad = 0, total_samples = 0;
+};
+
+inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int hop, GLPlanHost& P,
+                          std::string& err) {
+  if (win < 2 || win > NFFT || hop < 1 || hop > win) { err = "need 1 <= hop <= win <= n_fft"; return false; }
+  if ((NFFT - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
+  const int min_tile = min_tile_frames(win, hop);
+  if (min_tile > kTileFrames) { err = "win_length / hop_length > 8 is not supported"; return false; }
+  P.n_utts = n_utts; P.win = win; P.hop = hop;
+  P.frame_off.assign(frame_off, frame_off + n_utts + 1);
+  P.pad_off.assign(n_utts + 1, 0);
+  P.sample_off.assign(n_utts + 1, 0);
+  P.tiles.clear();
+  P.span_max = win;
+  P.max_tile = 1;
+  std::vector<std::pair<int, int> > parts;
+  for (int u = 0; u < n_utts; ++u) {
+    const long long T = frame_off[u + 1] - frame_off[u];
+    if (T < 1 || T > (1 << 22)) { err = "every utterance needs between 1 and 2^22 frames"; return false; }
+    const long long padded = NFFT + (long long)hop * (T - 1);
+    P.pad_off[u + 1] = P.pad_off[u] + ((padded + 3) & ~3LL);
+    P.sample_off[u + 1] = P.sample_off[u] + (long long)hop * (T - 1);
+    if (T < 2) continue;  // hop * (T - 1) == 0 output samples: nothing to compute
+    split_frames((int)T, kTileFrames, min_tile, parts);
+    for (size_t i = 0; i < parts.size(); ++i) {
+      GLTile t; t.utt = u; t.a = parts[i].first; t.b = parts[i].second; t.parity = (int)(i & 1);
+      P.tiles.push_back(t);
+      const int ft = t.b - t.a;
+      if (ft > P.max_tile) P.max_tile = ft;
+      const int span = (ft - 1) * hop + win;
+      if (span > P.span_max) P.span_max = span;
+    }
+  }
+  P.total_frames = frame_off[n_utts] - frame_off[0];
+  P.total_pad = P.pad_off[n_utts];
+  P.total_samples = P.sample_off[n_utts];
+  return true;
+}
+
+struct FeatPlanHost {
+  int n_clips = 0, win = 0, hop = 0, span_max = 0, reduction = 1;
+  std::vector<long long> sample_off, frame_off, row_off;
+  std::vector<FeatTile> tiles;
+  long long total_frames = 0, total_rows = 0;
+};
+
+inline bool build_feat_plan(int n_clips, const long long* sample_off, int win, int hop, int reduction,
+                            FeatPlanHost& P, std::string& err) {
+  if (win < 2 || win > NFFT || hop < 1) { err = "need hop >= 1 and 2 <= win <= n_fft"; return false; }
+  if ((NFFT - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
+  if (reduction < 1) reduction = 1;
+  P.n_clips = n_clips; P.win = win; P.hop = hop; P.reduction = reduction;
+  P.sample_off.assign(sample_off, sample_off + n_clips + 1);
+  P.frame_off.assign(n_clips + 1, 0);
+  P.row_off.assign(n_clips + 1, 0);
+  P.tiles.clear();
+  P.span_max = win;
+  for (int c = 0; c < n_clips; ++c) {
+    const long long N = sample_off[c + 1] - sample_off[c];
+    if (N < 1 || N > (1LL << 30)) { err = "every clip needs between 1 and 2^30 samples"; return false; }
+    const long long T = 1 + N / hop;
+    const long long rows = ((T + reduction - 1) / reduction) * reduction;
+    P.frame_off[c + 1] = P.frame_off[c] + T;
+    P.row_off[c + 1] = P.row_off[c] + rows;
+    for (long long a = 0; a < T; a += kTileFrames) {
+      FeatTile t; t.clip = c; t.a = (int)a; t.b = (int)((a + kTileFrames < T) ? a + kTileFrames : T);
+      t.last = (t.b == T) ? 1 : 0;
+      P.tiles.push_back(t);
+      const int span = (t.b - t.a - 1) * hop + win;
+      if (span > P.span_max) P.span_max = span;
+    }
+  }
+  P.total_frames = P.frame_off[n_clips];
+  P.total_rows = P.row_off[n_clips];
+  return true;
+}
+
+// Transform tables in double; callers narrow to the kernel's arithmetic type.
+inline void make_tables(int win, std::vector<double>& tw1024, std::vector<double>& w2048,
+                        std::vector<double>& window) {
+  const double pi = 3.14159265358979323846264338327950288;
+  tw1024.resize(2 * 1024);
+  for (int a = 0; a < 32; ++a)
+    for (int b = 0; b < 32; ++b) {
+      const int e = (a * b) % 1024;
+      tw1024[2 * (a * 32 + b)] = std::cos(2.0 * pi * e / 1024.0);
+      tw1024[2 * (a * 32 + b) + 1] = -std::sin(2.0 * pi * e / 1024.0);
+    }
+  w2048.resize(2 * 1024);
+  for (int k = 0; k < 1024; ++k) {
+    w2048[2 * k] = std::cos(2.0 * pi * k / 2048.0);
+    w2048[2 * k + 1] = -std::sin(2.0 * pi * k / 2048.0);
+  }
+  window.resize(win);
+  // scipy.signal.get_window('hann', win, fftbins=True): 0.5 - 0.5 cos(2 pi n / win)
+  for (int n = 0; n < win; ++n) window[n] = 0.5 - 0.5 * std::cos(2.0 * pi * n / win);
+}
+
+// librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=True, norm=1) (0.6.x), float64, as CSR
+// over mel bins (each filter's support is one contiguous run of FFT bins).
+// Used by the reference at audio/features.py:75-80.
+struct MelCSR {
+  std::vector<int> ptr, k0;
+  std::vector<double> w;
+};
+inline void make_mel_csr(int sr, int n_fft, int n_mels, double fmin, double fmax, MelCSR& M,
+                         std::vector<double>* dense = nullptr) {
+  const int n_bins = 1 + n_fft / 2;
+  std::vector<double> fftfreqs(n_bins), mel_f(n_mels + 2);
+  // np.linspace(0, sr / 2, n_bins): start + i * step
+  const double step = (double(sr) / 2.0) / (n_bins - 1);
+  for (int i = 0; i < n_bins; ++i) fftfreqs[i] = i * step;
+  fftfreqs[n_bins - 1] = double(sr) / 2.0;
+  const double mel_lo = 2595.0 * std::log10(1.0 + fmin / 700.0);
+  const double mel_hi = 2595.0 * std::log10(1.0 + fmax / 700.0);
+  const double mstep = (mel_hi - mel_lo) / (n_mels + 1);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    double m = mel_lo + i * mstep;
+    if (i == n_mels + 1) m = mel_hi;
+    mel_f[i] = 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
+  }
+  if (dense) dense->assign((size_t)n_mels * n_bins, 0.0);
+  M.ptr.assign(1, 0); M.k0.clear(); M.w.clear();
+  for (int i = 0; i < n_mels; ++i) {
+    const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    int first = -1, last = -1;
+    std::vector<double> row(n_bins);
+    for (int k = 0; k < n_bins; ++k) {
+      const double lower = -(mel_f[i] - fftfreqs[k]) / fd0;
+      const double upper = (mel_f[i + 2] - fftfreqs[k]) / fd1;
+      double v = lower < upper ? lower : upper;
+      if (v < 0.0) v = 0.0;
+      v *= enorm;
+      row[k] = v;
+      if (v != 0.0) { if (first < 0) first = k; last = k; }
+    }
+    if (first < 0) { first = 0; last = -1; }
+    M.k0.push_back(first);
+    for (int k = first; k <= last; ++k) M.w.push_back(row[k]);
+    M.ptr.push_back((int)M.w.size());
+    if (dense) for (int k = 0; k < n_bins; ++k) (*dense)[(size_t)i * n_bins + k] = row[k];
+  }
+}
+
+}  // namespace sstts

@@ -1,0 +1,459 @@
+// libsstts.so -- C ABI (include/sstts.h) over the sm_100a kernels in stft_kernels.cuh.
+//
+// Host side of the library: argument checking, tile/offset planning (host_plan.h), device
+// tables, kernel dispatch on (precision, geometry) and launch configuration.  No torch types,
+// no C++ exceptions across the boundary, no CPU fallback: without a CUDA device every compute
+// entry point fails with SSTTS_ERR_NO_DEVICE / SSTTS_ERR_CUDA.
+#include "../../include/sstts.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "host_plan.h"
+#include "stft_kernels.cuh"
+
+using namespace sstts;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? SSTTS_ERR_NO_DEVICE
+                                                                          : SSTTS_ERR_CUDA,
+              std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                             \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
+  } while (0)
+
+template <typename T>
+int upload(const std::vector<T>& h, T** d) {
+  *d = nullptr;
+  if (h.empty()) return 0;
+  CU(cudaMalloc((void**)d, h.size() * sizeof(T)));
+  CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Device copies of the transform tables in one precision.
+struct DeviceTables {
+  void* tw1024 = nullptr;
+  void* w2048 = nullptr;
+  void* window = nullptr;
+  void release() {
+    cudaFree(tw1024); cudaFree(w2048); cudaFree(window);
+    tw1024 = w2048 = window = nullptr;
+  }
+};
+
+template <typename T>
+int upload_tables(int win, DeviceTables& D) {
+  std::vector<double> tw, w2, wn;
+  make_tables(win, tw, w2, wn);
+  std::vector<T> a(tw.begin(), tw.end()), b(w2.begin(), w2.end()), c(wn.begin(), wn.end());
+  T *da, *db, *dc;
+  int rc;
+  if ((rc = upload(a, &da))) return rc;
+  D.tw1024 = da;
+  if ((rc = upload(b, &db))) return rc;
+  D.w2048 = db;
+  if ((rc = upload(c, &dc))) return rc;
+  D.window = dc;
+  return 0;
+}
+
+template <typename T>
+StftTables<T> tables_view(const DeviceTables& D) {
+  StftTables<T> t;
+  t.tw1024 = reinterpret_cast<const typename cx_of<T>::type*>(D.tw1024);
+  t.w2048 = reinterpret_cast<const typename cx_of<T>::type*>(D.w2048);
+  t.window = reinterpret_cast<const T*>(D.window);
+  return t;
+}
+
+int check_config(const sstts_stft_config* cfg) {
+  if (!cfg) return fail(SSTTS_ERR_INVALID, "config is NULL");
+  if (cfg->n_fft != NFFT) return fail(SSTTS_ERR_INVALID, "only n_fft = 2048 is built");
+  if (cfg->win_length < 2 || cfg->win_length > NFFT || ((NFFT - cfg->win_length) & 1))
+    return fail(SSTTS_ERR_INVALID, "win_length must be in [2, n_fft] with n_fft - win_length even");
+  if (cfg->hop_length < 1) return fail(SSTTS_ERR_INVALID, "hop_length must be >= 1");
+  if (cfg->precision != SSTTS_F32 && cfg->precision != SSTTS_F64)
+    return fail(SSTTS_ERR_INVALID, "precision must be SSTTS_F32 or SSTTS_F64");
+  return 0;
+}
+
+bool is_model_geometry(int win, int hop) { return win == 1102 && hop == 275; }
+typedef StaticGeom<1102, 275> ModelGeom;
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+template <typename K>
+int configure_kernel(K kernel, int threads, size_t smem, int* blocks_per_sm) {
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+  if (occ < 1) return fail(SSTTS_ERR_CUDA, "kernel does not fit on this device (shared memory / registers)");
+  *blocks_per_sm = occ;
+  return 0;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// plans
+// ----------------------------------------------------------------------------------------------
+struct sstts_gl_plan {
+  sstts_stft_config cfg;
+  GLPlanHost host;
+  DeviceTables tab;
+  long long* d_frame_off = nullptr;
+  long long* d_pad_off = nullptr;
+  long long* d_sample_off = nullptr;
+  GLTile* d_tiles = nullptr;
+  int device = 0;
+  int n_sms = 0;
+};
+
+struct sstts_feat_plan {
+  sstts_stft_config cfg;
+  FeatPlanHost host;
+  DeviceTables tab;
+  MelCSR mel;
+  std::vector<double> mel_dense;
+  long long* d_sample_off = nullptr;
+  long long* d_frame_off = nullptr;
+  long long* d_row_off = nullptr;
+  FeatTile* d_tiles = nullptr;
+  int* d_mel_ptr = nullptr;
+  int* d_mel_k0 = nullptr;
+  void* d_mel_w = nullptr;
+  int device = 0;
+  int n_sms = 0;
+};
+
+extern "C" {
+
+int sstts_version(void) { return SSTTS_VERSION; }
+const char* sstts_last_error(void) { return g_last_error.c_str(); }
+
+int sstts_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (n < 1) return fail(SSTTS_ERR_NO_DEVICE, "no CUDA device");
+  return n;
+}
+
+// ------------------------------------------------------------------------------ Griffin-Lim
+int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t* frame_off_host,
+                         sstts_gl_plan** plan_out) {
+  if (plan_out) *plan_out = nullptr;
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!plan_out || !frame_off_host || n_utts < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
+  sstts_gl_plan* P = new (std::nothrow) sstts_gl_plan();
+  if (!P) return fail(SSTTS_ERR_INVALID, "out of host memory");
+  P->cfg = *cfg;
+  std::string err;
+  std::vector<long long> fo(frame_off_host, frame_off_host + n_utts + 1);
+  if (!build_gl_plan(n_utts, fo.data(), cfg->win_length, cfg->hop_length, P->host, err)) {
+    delete P;
+    return fail(SSTTS_ERR_INVALID, err);
+  }
+  cudaError_t e = cudaGetDevice(&P->device);
+  if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
+  P->n_sms = sm_count();
+  rc = (cfg->precision == SSTTS_F64) ? upload_tables<double>(cfg->win_length, P->tab)
+                                     : upload_tables<float>(cfg->win_length, P->tab);
+  if (!rc) rc = upload(P->host.frame_off, &P->d_frame_off);
+  if (!rc) rc = upload(P->host.pad_off, &P->d_pad_off);
+  if (!rc) rc = upload(P->host.sample_off, &P->d_sample_off);
+  if (!rc) rc = upload(P->host.tiles, &P->d_tiles);
+  if (rc) { sstts_gl_plan_destroy(P); return rc; }
+  *plan_out = P;
+  return 0;
+}
+
+void sstts_gl_plan_destroy(sstts_gl_plan* P) {
+  if (!P) return;
+  P->tab.release();
+  cudaFree(P->d_frame_off); cudaFree(P->d_pad_off); cudaFree(P->d_sample_off); cudaFree(P->d_tiles);
+  delete P;
+}
+
+size_t sstts_gl_workspace_bytes(const sstts_gl_plan* P) {
+  if (!P) return 0;
+  const size_t elem = P->cfg.precision == SSTTS_F64 ? sizeof(double) : sizeof(float);
+  return 4 * (size_t)P->host.total_pad * elem + 256;
+}
+int64_t sstts_gl_total_frames(const sstts_gl_plan* P) { return P ? P->host.total_frames : 0; }
+int64_t sstts_gl_total_samples(const sstts_gl_plan* P) { return P ? P->host.total_samples : 0; }
+const int64_t* sstts_gl_sample_offsets(const sstts_gl_plan* P) {
+  return P ? reinterpret_cast<const int64_t*>(P->host.sample_off.data()) : nullptr;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T, typename G, int W>
+int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase0, int n_iter,
+                    void* workspace, float* wav_out, double* mse_frame, cudaStream_t st) {
+  const GLPlanHost& H = P->host;
+  if (H.tiles.empty()) return 0;
+  T* ws = reinterpret_cast<T*>(workspace);
+  T* buf[4] = {ws, ws + H.total_pad, ws + 2 * H.total_pad, ws + 3 * H.total_pad};
+
+  GLArgs<T> A;
+  A.mag = mag;
+  A.phase0 = reinterpret_cast<const float2*>(phase0);
+  A.frame_off = P->d_frame_off;
+  A.pad_off = P->d_pad_off;
+  A.tiles = P->d_tiles;
+  A.n_tiles = (int)H.tiles.size();
+  A.tab = tables_view<T>(P->tab);
+  A.mse_frame = nullptr;
+  A.win = H.win; A.hop = H.hop; A.span_max = H.span_max;
+
+  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.span_max);
+  int occ_s = 0, occ_i = 0, rc;
+  if ((rc = configure_kernel(gl_step_kernel<T, G, W, true>, W * 32, smem, &occ_s))) return rc;
+  if ((rc = configure_kernel(gl_step_kernel<T, G, W, false>, W * 32, smem, &occ_i))) return rc;
+  const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
+  int grid_s = n_sms * occ_s, grid_i = n_sms * occ_i;
+  if (grid_s > A.n_tiles) grid_s = A.n_tiles;
+  if (grid_i > A.n_tiles) grid_i = A.n_tiles;
+
+  // step 0: random phase -> wave_1 (written to buf[0], buf[1])
+  A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
+  gl_step_kernel<T, G, W, true><<<grid_s, W * 32, smem, st>>>(A);
+  CU(cudaGetLastError());
+  int cur = 0;
+  for (int it = 0; it < n_iter; ++it) {
+    A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
+    A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
+    A.mse_frame = (it == n_iter - 1) ? mse_frame : nullptr;
+    gl_step_kernel<T, G, W, false><<<grid_i, W * 32, smem, st>>>(A);
+    CU(cudaGetLastError());
+    cur ^= 1;
+  }
+  GLFinalArgs<T> F;
+  F.pin0 = buf[2 * cur]; F.pin1 = buf[2 * cur + 1];
+  F.frame_off = P->d_frame_off; F.pad_off = P->d_pad_off; F.sample_off = P->d_sample_off;
+  F.tiles = P->d_tiles; F.n_tiles = A.n_tiles;
+  F.window = A.tab.window;
+  F.wav_out = wav_out;
+  F.win = H.win; F.hop = H.hop;
+  int grid_f = n_sms * 8;
+  if (grid_f > A.n_tiles) grid_f = A.n_tiles;
+  gl_finalize_kernel<T, G, 256><<<grid_f, 256, sizeof(T) * H.win, st>>>(F);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// counter-based uniform phase: splitmix64 of (seed, index) -> 24-bit uniform -> unit phasor
+__global__ void random_phase_kernel(unsigned long long seed, long long n, float2* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // [0, 1)
+    float s, c;
+    sincospif(2.0f * u, &s, &c);
+    out[i] = make_float2(c, s);
+  }
+}
+
+__global__ void minmax_init_kernel(long long* mm, int n_clips) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_clips * 4) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
+}
+__global__ void minmax_decode_kernel(long long* mm, int n_clips) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_clips * 4) {
+    long long c = mm[i];
+    c = c >= 0 ? c : (c ^ 0x7fffffffffffffffLL);
+    reinterpret_cast<double*>(mm)[i] = __longlong_as_double(c);
+  }
+}
+
+template <typename T, typename G, int W>
+int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_outputs* O,
+                 cudaStream_t st) {
+  const FeatPlanHost& H = P->host;
+  FeatArgs<T> A;
+  A.wav = wav;
+  A.sample_off = P->d_sample_off; A.frame_off = P->d_frame_off; A.row_off = P->d_row_off;
+  A.tiles = P->d_tiles; A.n_tiles = (int)H.tiles.size();
+  A.tab = tables_view<T>(P->tab);
+  A.mel_ptr = P->d_mel_ptr; A.mel_k0 = P->d_mel_k0; A.mel_w = reinterpret_cast<const T*>(P->d_mel_w);
+  A.n_mels = P->cfg.n_mels;
+  A.spec_out = reinterpret_cast<float2*>(O->spec_dev);
+  A.lin_out = O->lin_db_dev;
+  A.mel_out = O->mel_db_dev;
+  A.melraw_out = O->mel_raw_dev;
+  A.minmax_out = reinterpret_cast<long long*>(O->minmax_dev);
+  // audio/conversion.py:78: the divisor abs(ref) + abs(max) is formed in Python floats.
+  A.lin_ref_db = (float)O->lin_ref_db;
+  A.lin_range_db = (float)(fabs(O->lin_ref_db) + fabs(O->lin_max_db));
+  A.mel_ref_db = O->mel_ref_db;
+  A.mel_range_db = fabs(O->mel_ref_db) + fabs(O->mel_max_db);
+  A.mel_power = (float)(O->mel_power == 0.0 ? 1.0 : O->mel_power);
+  A.normalize = O->normalize;
+  A.win = H.win; A.hop = H.hop; A.span_max = H.span_max;
+  if (A.n_mels < 1) { A.mel_out = nullptr; A.melraw_out = nullptr; }
+
+  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max);
+  int occ = 0, rc;
+  if ((rc = configure_kernel(stft_feature_kernel<T, G, W>, W * 32, smem, &occ))) return rc;
+  const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
+  int grid = n_sms * occ;
+  if (grid > A.n_tiles) grid = A.n_tiles;
+  if (A.minmax_out) {
+    const int n = H.n_clips * 4;
+    minmax_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(A.minmax_out, H.n_clips);
+    CU(cudaGetLastError());
+  }
+  stft_feature_kernel<T, G, W><<<grid, W * 32, smem, st>>>(A);
+  CU(cudaGetLastError());
+  if (A.minmax_out) {
+    const int n = H.n_clips * 4;
+    minmax_decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(A.minmax_out, H.n_clips);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sstts_griffin_lim(const sstts_gl_plan* P, const float* mag_dev, const float* phase0_dev,
+                      int n_iter, void* workspace_dev, float* wav_out_dev, double* mse_frame_dev,
+                      void* stream) {
+  if (!P || !mag_dev || !phase0_dev || !workspace_dev || n_iter < 0)
+    return fail(SSTTS_ERR_INVALID, "bad griffin_lim arguments");
+  if (P->host.total_samples > 0 && !wav_out_dev) return fail(SSTTS_ERR_INVALID, "wav_out_dev is NULL");
+  if (mse_frame_dev && n_iter < 1) return fail(SSTTS_ERR_INVALID, "mse needs n_iter >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool model = is_model_geometry(P->host.win, P->host.hop);
+  if (P->cfg.precision == SSTTS_F64) {
+    return model ? run_griffin_lim<double, ModelGeom, 4>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
+                                                         wav_out_dev, mse_frame_dev, st)
+                 : run_griffin_lim<double, DynGeom, 4>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
+                                                       wav_out_dev, mse_frame_dev, st);
+  }
+  return model ? run_griffin_lim<float, ModelGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
+                                                           wav_out_dev, mse_frame_dev, st)
+               : run_griffin_lim<float, DynGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
+                                                         wav_out_dev, mse_frame_dev, st);
+}
+
+int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
+  if (n < 0 || (n > 0 && !phase_dev)) return fail(SSTTS_ERR_INVALID, "bad random_phase arguments");
+  if (n == 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  random_phase_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      seed, n, reinterpret_cast<float2*>(phase_dev));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ features
+int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int64_t* sample_off_host,
+                           int reduction, sstts_feat_plan** plan_out) {
+  if (plan_out) *plan_out = nullptr;
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!plan_out || !sample_off_host || n_clips < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
+  if (cfg->n_mels < 0 || cfg->n_mels > 1024) return fail(SSTTS_ERR_INVALID, "n_mels out of range");
+  sstts_feat_plan* P = new (std::nothrow) sstts_feat_plan();
+  if (!P) return fail(SSTTS_ERR_INVALID, "out of host memory");
+  P->cfg = *cfg;
+  std::string err;
+  std::vector<long long> so(sample_off_host, sample_off_host + n_clips + 1);
+  if (!build_feat_plan(n_clips, so.data(), cfg->win_length, cfg->hop_length, reduction, P->host, err)) {
+    delete P;
+    return fail(SSTTS_ERR_INVALID, err);
+  }
+  cudaError_t e = cudaGetDevice(&P->device);
+  if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
+  P->n_sms = sm_count();
+  const bool f64 = cfg->precision == SSTTS_F64;
+  rc = f64 ? upload_tables<double>(cfg->win_length, P->tab) : upload_tables<float>(cfg->win_length, P->tab);
+  if (!rc && cfg->n_mels > 0) {
+    if (cfg->sampling_rate < 1) { sstts_feat_plan_destroy(P); return fail(SSTTS_ERR_INVALID, "sampling_rate must be > 0"); }
+    const double fmax = cfg->mel_fmax > 0 ? cfg->mel_fmax : cfg->sampling_rate / 2.0;
+    make_mel_csr(cfg->sampling_rate, cfg->n_fft, cfg->n_mels, cfg->mel_fmin, fmax, P->mel, &P->mel_dense);
+    rc = upload(P->mel.ptr, &P->d_mel_ptr);
+    if (!rc) rc = upload(P->mel.k0, &P->d_mel_k0);
+    if (!rc) {
+      if (f64) { double* d; rc = upload(P->mel.w, &d); P->d_mel_w = d; }
+      else { std::vector<float> wf(P->mel.w.begin(), P->mel.w.end()); float* d; rc = upload(wf, &d); P->d_mel_w = d; }
+    }
+  }
+  if (!rc) rc = upload(P->host.sample_off, &P->d_sample_off);
+  if (!rc) rc = upload(P->host.frame_off, &P->d_frame_off);
+  if (!rc) rc = upload(P->host.row_off, &P->d_row_off);
+  if (!rc) rc = upload(P->host.tiles, &P->d_tiles);
+  if (rc) { sstts_feat_plan_destroy(P); return rc; }
+  *plan_out = P;
+  return 0;
+}
+
+void sstts_feat_plan_destroy(sstts_feat_plan* P) {
+  if (!P) return;
+  P->tab.release();
+  cudaFree(P->d_sample_off); cudaFree(P->d_frame_off); cudaFree(P->d_row_off); cudaFree(P->d_tiles);
+  cudaFree(P->d_mel_ptr); cudaFree(P->d_mel_k0); cudaFree(P->d_mel_w);
+  delete P;
+}
+
+int64_t sstts_feat_total_frames(const sstts_feat_plan* P) { return P ? P->host.total_frames : 0; }
+int64_t sstts_feat_total_rows(const sstts_feat_plan* P) { return P ? P->host.total_rows : 0; }
+const int64_t* sstts_feat_frame_offsets(const sstts_feat_plan* P) {
+  return P ? reinterpret_cast<const int64_t*>(P->host.frame_off.data()) : nullptr;
+}
+const int64_t* sstts_feat_row_offsets(const sstts_feat_plan* P) {
+  return P ? reinterpret_cast<const int64_t*>(P->host.row_off.data()) : nullptr;
+}
+const double* sstts_feat_mel_basis(const sstts_feat_plan* P) {
+  return (P && !P->mel_dense.empty()) ? P->mel_dense.data() : nullptr;
+}
+
+int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const sstts_feat_outputs* out,
+                        void* stream) {
+  if (!P || !wav_dev || !out) return fail(SSTTS_ERR_INVALID, "bad stft_features arguments");
+  if ((out->mel_db_dev || out->mel_raw_dev) && P->cfg.n_mels < 1)
+    return fail(SSTTS_ERR_INVALID, "mel outputs requested but the plan has no filterbank");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool model = is_model_geometry(P->host.win, P->host.hop);
+  if (P->cfg.precision == SSTTS_F64)
+    return model ? run_features<double, ModelGeom, 4>(P, wav_dev, out, st)
+                 : run_features<double, DynGeom, 4>(P, wav_dev, out, st);
+  return model ? run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st)
+               : run_features<float, DynGeom, kWarps>(P, wav_dev, out, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,604 @@
+// sm_100a kernels for the audio hot path: Griffin-Lim iterations and the STFT feature pipeline.
+//
+// Common structure (both halves):
+//   * one WARP per frame: the n_fft = 2048 real transform is a 1024-point complex FFT held in
+//     the warp's registers (fft_warp.cuh), packed z[n] = x[2n] + i x[2n+1] and (un)tangled with
+//     the conjugate-pair identities below; the pair partner lives in lane (32 - l) & 31 and is
+//     exchanged with warp shuffles;
+//   * one CTA per TILE of consecutive frames of one utterance; the tile's sample span is staged
+//     in shared memory once (reflect padding resolved while staging), so every waveform sample
+//     crosses HBM/L2 once per tile although four to five frames overlap it;
+//   * persistent CTAs loop over a host-built tile table; ragged batches are packed with int64
+//     offset tables (frames, padded samples, output rows).
+//
+// Griffin-Lim (reference: audio/synthesis.py:91-123) is re-associated so that the state carried
+// between iterations is the overlap-added WAVEFORM instead of the complex spectrum:
+//     reference : angles -> istft -> stft -> angles          (x n_iter) -> istft
+//     here      : angles0 -> [synth] -> wave_1 ; wave_i -> [stft | E/|E| | x|S| | istft] ->
+//                 wave_(i+1)  (x n_iter) ; wave_(n_iter+1) is the reference's final istft.
+// The spectrum of a frame never leaves the warp's registers, so per frame and iteration only
+// |S| (4.1 KB) is read and ~1.2 KB of waveform is read and written.
+//
+// Overlap-add without atomics: inside a tile the warps drop their windowed frames into
+// per-warp shared-memory slots and all threads then GATHER, per output sample, the frames that
+// cover it in ascending frame order.  Across tiles the partially summed edge samples are
+// exchanged through two global buffers indexed by tile parity: a tile writes the raw sums of
+// its whole span into the buffer of its own parity, and a consumer adds the neighbour tile's
+// contribution from the other-parity buffer only inside the two edge regions where the
+// neighbour's frames reach in.  Tiles hold at least ceil(win/hop) - 1 (>= 4) frames, which makes
+// same-parity spans disjoint and the left/right edge regions of a tile disjoint.
+#pragma once
+#include "fft_warp.cuh"
+
+namespace sstts {
+
+constexpr int NFFT = 2048;
+constexpr int HALF = NFFT / 2;     // centre padding, and #complex points of the packed FFT
+constexpr int NBINS = HALF + 1;    // 1025
+
+// ---------------------------------------------------------------------------------------------
+// geometry policies: compile-time (win, hop) for the model configuration, run-time otherwise
+// ---------------------------------------------------------------------------------------------
+template <int WIN, int HOP> struct StaticGeom {
+  SSTTS_HD StaticGeom(int, int) {}
+  SSTTS_HD constexpr int win() const { return WIN; }
+  SSTTS_HD constexpr int hop() const { return HOP; }
+  SSTTS_HD constexpr int lpad() const { return (NFFT - WIN) / 2; }
+};
+struct DynGeom {
+  int win_, hop_;
+  SSTTS_HD DynGeom(int w, int h) : win_(w), hop_(h) {}
+  SSTTS_HD int win() const { return win_; }
+  SSTTS_HD int hop() const { return hop_; }
+  SSTTS_HD int lpad() const { return (NFFT - win_) / 2; }
+};
+
+// numpy.pad(mode='reflect') index map for any q (multi-bounce for short signals).
+SSTTS_HD int reflect_index(int q, int L) {
+  if (L <= 1) return 0;
+  const int period = 2 * (L - 1);
+  int m = q % period;
+  if (m < 0) m += period;
+  return m < L ? m : period - m;
+}
+
+SSTTS_HD int round_up4(int v) { return (v + 3) & ~3; }
+
+template <typename T> struct StftTables {
+  const typename cx_of<T>::type* tw1024;  // [32*32]  exp(-2 pi i a b / 1024) at [a*32+b]
+  const typename cx_of<T>::type* w2048;   // [1024]   exp(-2 pi i k / 2048)
+  const T* window;                        // [win]    periodic Hann (float64 -> T)
+};
+
+// Sum over the frames t in [0, n_frames) covering padded coordinate p of window(p - t hop)^2,
+// ascending t (librosa.filters.window_sumsquare restricted to one sample).
+template <typename T>
+SSTTS_D T window_sumsq(int p, int n_frames, int hop, int win, int lpad, const T* s_win) {
+  const int x = p - lpad;
+  if (x < 0) return T(0);
+  int t_hi = x / hop;
+  if (t_hi > n_frames - 1) t_hi = n_frames - 1;
+  const int num = x - win + 1;
+  const int t_lo = num <= 0 ? 0 : (num + hop - 1) / hop;
+  T acc = T(0);
+  for (int t = t_lo; t <= t_hi; ++t) {
+    const T w = s_win[x - t * hop];
+    acc += w * w;
+  }
+  return acc;
+}
+
+// np.finfo(np.float32).tiny -- librosa's guard for the window-sum division.
+#define SSTTS_F32_TINY 1.17549435e-38f
+
+// =============================================================================================
+// Griffin-Lim
+// =============================================================================================
+struct GLTile { int utt, a, b, parity; };  // frames [a, b) of utterance utt
+
+template <typename T> struct GLArgs {
+  const float* mag;              // (sum T, 1025) frame-major |S|
+  const float2* phase0;          // (sum T, 1025) initial unit phasors (FROM_PHASE launch only)
+  const T* pin0; const T* pin1;  // partial overlap-add sums of the previous step, by tile parity
+  T* pout0; T* pout1;            // ... of this step
+  const long long* frame_off;    // [n_utts + 1]
+  const long long* pad_off;      // [n_utts + 1] offsets of each utterance's padded axis
+  const GLTile* tiles;
+  int n_tiles;
+  StftTables<T> tab;
+  double* mse_frame;             // [sum T] per-frame sum_k (|S| - |E|)^2 or nullptr
+  int win, hop, span_max;
+};
+
+template <typename T> SSTTS_D T fast_rsqrt(T x);
+template <> SSTTS_D float fast_rsqrt<float>(float x) { return rsqrtf(x); }
+template <> SSTTS_D double fast_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
+
+// Unit phasor of (xr, xi) times s;  (1, 0) * s when the bin is exactly zero
+// (np.exp(1j * np.angle(0)) == 1, audio/synthesis.py:109).
+template <typename T>
+SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
+  m2 = xr * xr + xi * xi;
+  if (m2 > T(0)) {
+    const T inv = fast_rsqrt<T>(m2) * s;
+    yr = xr * inv; yi = xi * inv;
+  } else {
+    yr = s; yi = T(0);
+  }
+}
+
+// The per-frame core of one Griffin-Lim step, on the packed spectrum held by the warp.
+//   in  (FROM_PHASE = false): re/im = Z = FFT1024(z) in bit-reversed slots
+//   out: re/im = 2 Z' (packed spectrum of |S| * E/|E|) in bit-reversed slots
+// Conjugate-pair identities (N = 1024, w = exp(-2 pi i k / 2048), Zn = Z[N-k]):
+//   2 X[k]   = (Zk + conj Zn) + w * (-i)(Zk - conj Zn)
+//   2 X[N-k] = conj((Zk + conj Zn) - w * (-i)(Zk - conj Zn))
+//   2 Z'[k]   = (Yk + conj Yn) + i conj(w) (Yk - conj Yn)          (Y = |S| X/|X|)
+//   2 Z'[N-k] = conj(Yk + conj Yn) + i conj(conj(w) (Yk - conj Yn))
+// Lane l owns k = l + 32 k2; for k2 < 16 its partner bin N - k sits in lane (32 - l) & 31,
+// slot 31 - k2 (lane 0: its own slot 32 - k2; k = 0 pairs with the Nyquist bin; k = 512 is
+// self-conjugate).  Each lane processes its 16 low pairs and swaps results with its partner.
+template <typename T, bool FROM_PHASE>
+SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ mrow,
+                           const float2* __restrict__ prow,
+                           const typename cx_of<T>::type* s_w2k, int lane, bool want_mse,
+                           double& mse_acc) {
+  typedef typename cx_of<T>::type C;
+  const int partner = (32 - lane) & 31;
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const int sl_mine = brev5(k2);
+    const int sl_part = brev5(31 - k2);
+    const int sl_alt = brev5((32 - k2) & 31);
+    const int k = lane + 32 * k2;
+    const int kn = HALF - k;
+    const C w = s_w2k[k];
+    const T sk = fabs((T)mrow[k]);
+    const T sn = fabs((T)mrow[kn]);
+    T ykr, yki, ynr, yni;
+    if (!FROM_PHASE) {
+      const T zr = re[sl_mine], zi = im[sl_mine];
+      T pr = __shfl_sync(0xffffffffu, re[sl_part], partner);
+      T pi = __shfl_sync(0xffffffffu, im[sl_part], partner);
+      if (lane == 0) { pr = re[sl_alt]; pi = im[sl_alt]; }
+      const T er = zr + pr, ei = zi - pi;   // Zk + conj Zn
+      const T dr = zr - pr, di = zi + pi;   // Zk - conj Zn
+      const T wor = w.x * di + w.y * dr;    // w * (di - i dr)
+      const T woi = w.y * di - w.x * dr;
+      const T xkr = er + wor, xki = ei + woi;      // 2 X[k]
+      const T xnr = er - wor, xni = woi - ei;      // 2 X[N-k]
+      T m2k, m2n;
+      replace_magnitude<T>(xkr, xki, sk, ykr, yki, m2k);
+      replace_magnitude<T>(xnr, xni, sn, ynr, yni, m2n);
+      if (want_mse) {
+        const double ek = (double)sk - 0.5 * sqrt((double)m2k);
+        const double en = (double)sn - 0.5 * sqrt((double)m2n);
+        mse_acc += ek * ek + en * en;
+      }
+    } else {
+      const float2 pk = prow[k], pn = prow[kn];
+      ykr = sk * (T)pk.x; yki = sk * (T)pk.y;
+      ynr = sn * (T)pn.x; yni = sn * (T)pn.y;
+      if (lane == 0 && k2 == 0) { yki = T(0); yni = T(0); }  // ifft(...).real drops Im of DC/Nyquist
+    }
+    const T e2r = ykr + ynr, e2i = yki - yni;   // Yk + conj Yn
+    const T d2r = ykr - ynr, d2i = yki + yni;   // Yk - conj Yn
+    const T o2r = w.x * d2r + w.y * d2i;        // conj(w) * (Yk - conj Yn)
+    const T o2i = w.x * d2i - w.y * d2r;
+    const T zkr = e2r - o2i, zki = e2i + o2r;   // 2 Z'[k]
+    const T znr = e2r + o2i, zni = o2r - e2i;   // 2 Z'[N-k]
+    const T rr = __shfl_sync(0xffffffffu, znr, partner);
+    const T ri = __shfl_sync(0xffffffffu, zni, partner);
+    re[sl_mine] = zkr; im[sl_mine] = zki;
+    if (lane == 0) {
+      if (k2 != 0) { re[sl_alt] = znr; im[sl_alt] = zni; }
+    } else {
+      re[sl_part] = rr; im[sl_part] = ri;
+    }
+  }
+  // k = 512 (lane 0, slot 16): X = conj(Z), Z' = conj(Y).
+  if (lane == 0) {
+    const int sl = brev5(16);
+    const T s = fabs((T)mrow[HALF / 2]);
+    T yr, yi;
+    if (!FROM_PHASE) {
+      T m2;
+      replace_magnitude<T>(T(2) * re[sl], T(-2) * im[sl], s, yr, yi, m2);
+      if (want_mse) {
+        const double e = (double)s - 0.5 * sqrt((double)m2);
+        mse_acc += e * e;
+      }
+    } else {
+      const float2 p = prow[HALF / 2];
+      yr = s * (T)p.x; yi = s * (T)p.y;
+    }
+    re[sl] = T(2) * yr; im[sl] = T(-2) * yi;
+  }
+}
+
+// One Griffin-Lim step over all tiles.  FROM_PHASE = true is the initial synthesis from the
+// random phase (no analysis half).  W warps per CTA, one frame per warp per round.
+template <typename T, typename G, int W, bool FROM_PHASE>
+__global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
+  typedef typename cx_of<T>::type C;
+  const G g(A.win, A.hop);
+  const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NT = W * 32;
+
+  SSTTS_DYN_SMEM(smem);
+  C* s_tw = reinterpret_cast<C*>(smem);
+  C* s_w2k = s_tw + 1024;
+  C* s_xt = s_w2k + 1024;
+  T* s_win = reinterpret_cast<T*>(s_xt + W * XTILE_ELEMS);
+  T* s_yin = s_win + round_up4(win);
+  T* s_yout = s_yin + round_up4(A.span_max);
+
+  for (int i = tid; i < 1024; i += NT) { s_tw[i] = A.tab.tw1024[i]; s_w2k[i] = A.tab.w2048[i]; }
+  for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
+  __syncthreads();
+
+  C* xt = s_xt + warp * XTILE_ELEMS;
+  const T syn_scale = T(1.0 / NFFT);
+
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    const GLTile tl = A.tiles[tile];
+    const long long f0 = A.frame_off[tl.utt];
+    const int n_frames = (int)(A.frame_off[tl.utt + 1] - f0);
+    const long long poff = A.pad_off[tl.utt];
+    const int a = tl.a, b = tl.b, FT = b - a;
+    const int L = hop * (n_frames - 1);
+    const int span_lo = a * hop + lpad;
+    const int span = (FT - 1) * hop + win;
+    const T* pin_own = (tl.parity ? A.pin1 : A.pin0) + poff;
+    const T* pin_oth = (tl.parity ? A.pin0 : A.pin1) + poff;
+    T* pout_own = (tl.parity ? A.pout1 : A.pout0) + poff;
+
+    if (!FROM_PHASE) {
+      // Stage the analysis input x_pad[span] = y_norm[reflect], y_norm = OLA sum / window sum.
+      const int left_end = (a - 1) * hop + lpad + win;   // previous tile reaches below this
+      const int right_beg = b * hop + lpad;              // next tile reaches from here
+      for (int s = tid; s < span; s += NT) {
+        int q = span_lo + s - HALF;
+        if (q < 0 || q >= L) q = reflect_index(q, L);
+        const int p = q + HALF;
+        T v = pin_own[p];
+        if (a > 0 && p < left_end) v += pin_oth[p];
+        if (b < n_frames && p >= right_beg) v += pin_oth[p];
+        const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
+        if (wss > T(SSTTS_F32_TINY)) v = v / wss;
+        s_yin[s] = v;
+      }
+    }
+    for (int s = tid; s < span; s += NT) s_yout[s] = T(0);
+    __syncthreads();
+
+    const int n_rounds = (FT + W - 1) / W;
+    for (int r = 0; r < n_rounds; ++r) {
+      const int jr = r * W + warp;
+      if (jr < FT) {
+        const long long row = f0 + a + jr;
+        const float* mrow = A.mag + row * NBINS;
+        const float2* prow = FROM_PHASE ? A.phase0 + row * NBINS : nullptr;
+        T re[32], im[32];
+        if (!FROM_PHASE) {
+          const T* fin = s_yin + jr * hop - lpad;  // fin[m], m in [lpad, lpad + win)
+#pragma unroll
+          for (int n1 = 0; n1 < 32; ++n1) {
+            const int m = 64 * n1 + 2 * lane;
+            const int i = m - lpad;
+            re[n1] = (i >= 0 && i < win) ? fin[m] * s_win[i] : T(0);
+            im[n1] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * s_win[i + 1] : T(0);
+          }
+          warp_fft1024<T, false, false>(re, im, xt, s_tw, lane);
+        }
+        double mse_acc = 0.0;
+        const bool want_mse = (!FROM_PHASE) && (A.mse_frame != nullptr);
+        gl_frame_core<T, FROM_PHASE>(re, im, mrow, prow, s_w2k, lane, want_mse, mse_acc);
+        if (want_mse) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
+          if (lane == 0) A.mse_frame[row] = mse_acc;
+        }
+        warp_fft1024<T, true, true>(re, im, xt, s_tw, lane);
+        T* slot = reinterpret_cast<T*>(xt);  // the transpose tile is dead now: reuse as frame slot
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int i = 64 * n1 + 2 * lane - lpad;
+          if (i >= 0 && i < win) slot[i] = re[n1] * (s_win[i] * syn_scale);
+          if (i + 1 >= 0 && i + 1 < win) slot[i + 1] = im[n1] * (s_win[i + 1] * syn_scale);
+        }
+      }
+      __syncthreads();
+      // Gather-accumulate this round's frames into the tile's overlap-add buffer.
+      const int jr0 = r * W;
+      const int jr1 = (jr0 + W < FT) ? jr0 + W : FT;
+      const int s_hi = (jr1 - 1) * hop + win;
+      for (int s = jr0 * hop + tid; s < s_hi; s += NT) {
+        int f_hi = s / hop;
+        if (f_hi > jr1 - 1) f_hi = jr1 - 1;
+        const int num = s - win + 1;
+        int f_lo = num <= 0 ? 0 : (num + hop - 1) / hop;
+        if (f_lo < jr0) f_lo = jr0;
+        T acc = s_yout[s];
+        for (int f = f_lo; f <= f_hi; ++f)
+          acc += reinterpret_cast<const T*>(s_xt + (f - jr0) * XTILE_ELEMS)[s - f * hop];
+        s_yout[s] = acc;
+      }
+      __syncthreads();
+    }
+    for (int s = tid; s < span; s += NT) pout_own[span_lo + s] = s_yout[s];
+    __syncthreads();
+  }
+}
+
+template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int span_max) {
+  return sizeof(typename cx_of<T>::type) * (size_t)(2048 + warps * XTILE_ELEMS) +
+         sizeof(T) * (size_t)(round_up4(win) + 2 * round_up4(span_max));
+}
+
+// Partial sums -> normalised, centre-trimmed float32 waveform (the reference's final istft
+// epilogue: divide by the window sum where > tiny, drop n_fft/2 samples on both sides).
+template <typename T> struct GLFinalArgs {
+  const T* pin0; const T* pin1;
+  const long long* frame_off; const long long* pad_off; const long long* sample_off;
+  const GLTile* tiles; int n_tiles;
+  const T* window;
+  float* wav_out;
+  int win, hop;
+};
+
+template <typename T, typename G, int NT>
+__global__ void __launch_bounds__(NT) gl_finalize_kernel(const GLFinalArgs<T> A) {
+  const G g(A.win, A.hop);
+  const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const int tid = threadIdx.x;
+  SSTTS_DYN_SMEM(smem);
+  T* s_win = reinterpret_cast<T*>(smem);
+  for (int i = tid; i < win; i += NT) s_win[i] = A.window[i];
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    const GLTile tl = A.tiles[tile];
+    const long long f0 = A.frame_off[tl.utt];
+    const int n_frames = (int)(A.frame_off[tl.utt + 1] - f0);
+    const long long poff = A.pad_off[tl.utt];
+    const int L = hop * (n_frames - 1);
+    const int a = tl.a, b = tl.b;
+    const T* pin_own = (tl.parity ? A.pin1 : A.pin0) + poff;
+    const T* pin_oth = (tl.parity ? A.pin0 : A.pin1) + poff;
+    float* out = A.wav_out + A.sample_off[tl.utt];
+    int p_lo = a * hop + lpad;
+    if (p_lo < HALF) p_lo = HALF;
+    int p_hi = (b < n_frames) ? b * hop + lpad : HALF + L;
+    if (p_hi > HALF + L) p_hi = HALF + L;
+    const int left_end = (a - 1) * hop + lpad + win;
+    for (int p = p_lo + tid; p < p_hi; p += NT) {
+      T v = pin_own[p];
+      if (a > 0 && p < left_end) v += pin_oth[p];
+      const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
+      if (wss > T(SSTTS_F32_TINY)) v = v / wss;
+      out[p - HALF] = (float)v;
+    }
+  }
+}
+
+// =============================================================================================
+// STFT feature pipeline
+// =============================================================================================
+struct FeatTile { int clip, a, b, last; };  // frames [a, b) of clip; last = tile holds frame T-1
+
+template <typename T> struct FeatArgs {
+  const float* wav;               // packed clips
+  const long long* sample_off;    // [n_clips + 1]
+  const long long* frame_off;     // [n_clips + 1] (frame counts T = 1 + N / hop)
+  const long long* row_off;       // [n_clips + 1] output row offsets (>= frames: zero pad rows)
+  const FeatTile* tiles;
+  int n_tiles;
+  StftTables<T> tab;
+  const int* mel_ptr;             // [n_mels + 1] CSR row pointers
+  const int* mel_k0;              // [n_mels]     first FFT bin of each mel filter
+  const T* mel_w;                 // [nnz]        filter weights (float64 -> T)
+  int n_mels;
+  float2* spec_out;               // (rows, 1025) complex64 STFT, or nullptr
+  float* lin_out;                 // (rows, 1025) linear dB (normalised if normalize), or nullptr
+  float* mel_out;                 // (rows, n_mels) mel dB (normalised if normalize), or nullptr
+  double* melraw_out;             // (rows, n_mels) mel_basis @ |S|**power, or nullptr
+  long long* minmax_out;          // [n_clips * 4] order-preserving int64 codes of
+                                  //   (min lin dB, max lin dB, min mel dB, max mel dB), or nullptr
+  float lin_ref_db, lin_range_db; // normalisation constants: ref, |ref| + |max|
+  double mel_ref_db, mel_range_db;
+  float mel_power;
+  int normalize;
+  int win, hop, span_max;
+};
+
+SSTTS_D long long encode_ordered(double v) {
+  long long b;
+#ifdef SSTTS_CPU_EMU
+  std::memcpy(&b, &v, 8);
+#else
+  b = __double_as_longlong(v);
+#endif
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+
+template <typename T> struct feat_math;
+template <> struct feat_math<float> {
+  // |complex64| and 20 log10(max(1e-5, .)) in float32 (audio/conversion.py:29 on float32 input).
+  static SSTTS_D float magnitude(float xr, float xi) { return sqrtf(xr * xr + xi * xi); }
+  static SSTTS_D float mel_db(float m) { return 20.0f * log10f(fmaxf(1e-5f, m)); }
+};
+template <> struct feat_math<double> {
+  // float64 transform rounded to complex64 like librosa's stft_matrix, then |.| in float32.
+  static SSTTS_D float magnitude(double xr, double xi) {
+    const double fr = (double)(float)xr, fi = (double)(float)xi;
+    return (float)sqrt(fr * fr + fi * fi);
+  }
+  static SSTTS_D double mel_db(double m) { return 20.0 * log10(fmax(1e-5, m)); }
+};
+
+template <typename T, typename G, int W>
+__global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> A) {
+  typedef typename cx_of<T>::type C;
+  const G g(A.win, A.hop);
+  const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NT = W * 32;
+
+  SSTTS_DYN_SMEM(smem);
+  C* s_tw = reinterpret_cast<C*>(smem);
+  C* s_w2k = s_tw + 1024;
+  C* s_xt = s_w2k + 1024;
+  T* s_win = reinterpret_cast<T*>(s_xt + W * XTILE_ELEMS);
+  float* s_x = reinterpret_cast<float*>(s_win + round_up4(win));
+
+  for (int i = tid; i < 1024; i += NT) { s_tw[i] = A.tab.tw1024[i]; s_w2k[i] = A.tab.w2048[i]; }
+  for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
+  __syncthreads();
+
+  C* xt = s_xt + warp * XTILE_ELEMS;
+  const bool want_lin = A.lin_out != nullptr;
+  const bool want_mel = (A.mel_out != nullptr) || (A.melraw_out != nullptr) ||
+                        (A.minmax_out != nullptr);
+
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    const FeatTile tl = A.tiles[tile];
+    const long long soff = A.sample_off[tl.clip];
+    const int n_samples = (int)(A.sample_off[tl.clip + 1] - soff);
+    const long long f0 = A.frame_off[tl.clip];
+    const int n_frames = (int)(A.frame_off[tl.clip + 1] - f0);
+    const long long r0 = A.row_off[tl.clip];
+    const int n_rows = (int)(A.row_off[tl.clip + 1] - r0);
+    const int a = tl.a, b = tl.b, FT = b - a;
+    const int span_lo = a * hop + lpad;
+    const int span = (FT - 1) * hop + win;
+    const float* x = A.wav + soff;
+
+    for (int s = tid; s < span; s += NT) {
+      int q = span_lo + s - HALF;
+      if (q < 0 || q >= n_samples) q = reflect_index(q, n_samples);
+      s_x[s] = x[q];
+    }
+    // zero rows appended by apply_reduction_padding (datasets/dataset_helper.py:383-393)
+    if (tl.last && n_rows > n_frames) {
+      const long long zr0 = r0 + n_frames;
+      const int nz = n_rows - n_frames;
+      if (A.lin_out) for (int i = tid; i < nz * NBINS; i += NT) A.lin_out[zr0 * NBINS + i] = 0.0f;
+      if (A.mel_out) for (int i = tid; i < nz * A.n_mels; i += NT) A.mel_out[zr0 * A.n_mels + i] = 0.0f;
+    }
+    __syncthreads();
+
+    double mn_lin = 1e300, mx_lin = -1e300, mn_mel = 1e300, mx_mel = -1e300;
+    for (int jr = warp; jr < FT; jr += W) {
+      const long long row = r0 + a + jr;
+      T re[32], im[32];
+      const float* fin = s_x + jr * hop - lpad;
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const int m = 64 * n1 + 2 * lane;
+        const int i = m - lpad;
+        re[n1] = (i >= 0 && i < win) ? (T)fin[m] * s_win[i] : T(0);
+        im[n1] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * s_win[i + 1] : T(0);
+      }
+      warp_fft1024<T, false, false>(re, im, xt, s_tw, lane);
+      __syncwarp();
+      float* s_mag = reinterpret_cast<float*>(xt);  // transpose tile is dead: |S| of this frame
+      const int partner = (32 - lane) & 31;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const int sl_mine = brev5(k2);
+        const int sl_part = brev5(31 - k2);
+        const int sl_alt = brev5((32 - k2) & 31);
+        const int k = lane + 32 * k2;
+        const int kn = HALF - k;
+        const C w = s_w2k[k];
+        const T zr = re[sl_mine], zi = im[sl_mine];
+        T pr = __shfl_sync(0xffffffffu, re[sl_part], partner);
+        T pi = __shfl_sync(0xffffffffu, im[sl_part], partner);
+        if (lane == 0) { pr = re[sl_alt]; pi = im[sl_alt]; }
+        const T er = zr + pr, ei = zi - pi;
+        const T dr = zr - pr, di = zi + pi;
+        const T wor = w.x * di + w.y * dr;
+        const T woi = w.y * di - w.x * dr;
+        const T xkr = T(0.5) * (er + wor), xki = T(0.5) * (ei + woi);   // X[k]
+        const T xnr = T(0.5) * (er - wor), xni = T(0.5) * (woi - ei);   // X[N-k]
+        if (A.spec_out) {
+          A.spec_out[row * NBINS + k] = make_float2((float)xkr, (float)xki);
+          A.spec_out[row * NBINS + kn] = make_float2((float)xnr, (float)xni);
+        }
+        s_mag[k] = feat_math<T>::magnitude(xkr, xki);
+        s_mag[kn] = feat_math<T>::magnitude(xnr, xni);
+      }
+      if (lane == 0) {
+        const int sl = brev5(16);
+        if (A.spec_out) A.spec_out[row * NBINS + HALF / 2] = make_float2((float)re[sl], (float)(-im[sl]));
+        s_mag[HALF / 2] = feat_math<T>::magnitude(re[sl], -im[sl]);
+      }
+      __syncwarp();
+      if (want_lin || A.minmax_out) {
+        for (int k = lane; k < NBINS; k += 32) {
+          const float db = 20.0f * log10f(fmaxf(1e-5f, s_mag[k]));
+          mn_lin = fmin(mn_lin, (double)db);
+          mx_lin = fmax(mx_lin, (double)db);
+          if (want_lin) {
+            float v = db;
+            if (A.normalize) {
+              v = 1.0f + (db - A.lin_ref_db) / A.lin_range_db;
+              v = fminf(fmaxf(v, 0.0f), 1.0f);
+            }
+            A.lin_out[row * NBINS + k] = v;
+          }
+        }
+      }
+      if (want_mel) {
+        for (int m = lane; m < A.n_mels; m += 32) {
+          const int p0 = A.mel_ptr[m], p1 = A.mel_ptr[m + 1];
+          const float* mg = s_mag + A.mel_k0[m];
+          T acc = T(0);
+          for (int i = p0; i < p1; ++i) {
+            float sm = mg[i - p0];
+            if (A.mel_power != 1.0f) sm = (A.mel_power == 2.0f) ? sm * sm : powf(sm, A.mel_power);
+            acc += A.mel_w[i] * (T)sm;
+          }
+          if (A.melraw_out) A.melraw_out[row * A.n_mels + m] = (double)acc;
+          const T db = feat_math<T>::mel_db(acc < T(0) ? -acc : acc);
+          mn_mel = fmin(mn_mel, (double)db);
+          mx_mel = fmax(mx_mel, (double)db);
+          if (A.mel_out) {
+            T v = db;
+            if (A.normalize) {
+              v = T(1) + (db - (T)A.mel_ref_db) / (T)A.mel_range_db;
+              v = v < T(0) ? T(0) : (v > T(1) ? T(1) : v);
+            }
+            A.mel_out[row * A.n_mels + m] = (float)v;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (A.minmax_out) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn_lin = fmin(mn_lin, __shfl_xor_sync(0xffffffffu, mn_lin, o));
+        mx_lin = fmax(mx_lin, __shfl_xor_sync(0xffffffffu, mx_lin, o));
+        mn_mel = fmin(mn_mel, __shfl_xor_sync(0xffffffffu, mn_mel, o));
+        mx_mel = fmax(mx_mel, __shfl_xor_sync(0xffffffffu, mx_mel, o));
+      }
+      if (lane == 0 && warp < FT) {
+        long long* mm = A.minmax_out + 4LL * tl.clip;
+        atomicMin(mm + 0, encode_ordered(mn_lin));
+        atomicMax(mm + 1, encode_ordered(mx_lin));
+        atomicMin(mm + 2, encode_ordered(mn_mel));
+        atomicMax(mm + 3, encode_ordered(mx_mel));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T> SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max) {
+  return sizeof(typename cx_of<T>::type) * (size_t)(2048 + warps * XTILE_ELEMS) +
+         sizeof(T) * (size_t)round_up4(win) + sizeof(float) * (size_t)round_up4(span_max);
+}
+
+}  // namespace sstts
