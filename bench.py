@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the audio hot path (BASELINE.json): batched 50-iteration Griffin-Lim and the
+STFT feature pipeline, in audio-seconds per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" is one pass of the hot path over one batch: BASELINE configs[2] -- Griffin-Lim, 50
+iterations, 256 ragged synthetic utterances (1-10 s, 22.05 kHz) per GPU -- which is the primary
+metric; the feature pipeline (configs[1], the same 256 clips) is measured in the same run and
+reported under "features".  `value` is device-resident throughput (inputs in HBM when the timed
+region starts, launched through the C ABI), `e2e` goes through the public Python API with host
+numpy buffers (pinned staging, H2D, kernels, D2H inside the timed region).  Weak scaling: every
+rank owns its own 256 utterances; no data-path collective (utterances are independent).
+
+--impl reference times the reference's CPU implementation of the same path (the numpy oracle
+restating librosa 0.6 + audio/synthesis.py; the reference itself cannot be installed: librosa and
+TensorFlow 1.8 are unavailable offline) on all host cores on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics as pystats
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIN, HOP, NFFT, SR = 1102, 275, 2048, 22050
+N_BINS = 1025
+N_UTTS = 256
+GL_ITERS = 50
+# algorithmic bytes per frame and Griffin-Lim iteration
+# (phase read + |S| read + phase write + waveform write + waveform read).
+GL_BYTES_PER_FRAME_ITER = 22700
+GL_BYTES_FINAL_PER_FRAME = 13400
+FEAT_BYTES_PER_FRAME = 4420   # (1025 + 80) float32 written per frame; + 4 bytes per input sample
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': pystats.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on host cores
+# ------------------------------------------------------------------------------------------------
+def _oracle_gl_worker(args):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    os.environ['MKL_NUM_THREADS'] = '1'
+    sys.path.insert(0, ROOT)
+    from oracle import reference_audio as ra
+    mag, seed = args
+    angles = np.exp(2j * np.pi * np.random.RandomState(seed).rand(*mag.shape))
+    wav = ra.spectrogram_to_wav(mag, WIN, HOP, NFFT, GL_ITERS, angles=angles)
+    return len(wav)
+
+
+def oracle_sample(n_items, seconds, seed):
+    """Bounded sample of the workload: n_items synthetic clips of `seconds` s -> |STFT|."""
+    from oracle import librosa_compat as lc
+    from single_speaker_tts_b200.synthetic import speech_like_clip
+    rng = np.random.default_rng(seed)
+    mags = []
+    for _ in range(n_items):
+        x = speech_like_clip(int(seconds * SR), rng)
+        mags.append(np.abs(lc.stft(x, NFFT, HOP, WIN)))
+    return mags
+
+
+def time_oracle_gl(pool, mags, seed0):
+    t0 = time.perf_counter()
+    lens = pool.map(_oracle_gl_worker, [(m, seed0 + i) for i, m in enumerate(mags)])
+    dt = time.perf_counter() - t0
+    return sum(lens) / SR, dt
+
+
+def run_reference(args):
+    """--impl reference: the oracle (kind "port": the reference's numpy/librosa code restated; the
+    reference itself is not installable offline) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    sample_s = 3.0
+    mags = oracle_sample(cores, sample_s, seed=2)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            time_oracle_gl(pool, mags[:cores], 1000)
+        audio, total = 0.0, 0.0
+        for s in range(args.steps):
+            a, dt = time_oracle_gl(pool, mags, 1000 + s)
+            audio += a
+            total += dt
+    value = audio / total
+    sample = '{} utterances x {:.0f} s per step, one process per core, {} iterations'.format(
+        cores, sample_s, GL_ITERS)
+    line = {
+        'impl': 'reference', 'metric': 'griffin_lim_50it_audio_sec_per_sec', 'value': value,
+        'unit': 'audio-s/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1000.0 * total / max(1, args.steps), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[2]: Griffin-Lim 50 it, ragged synthetic utterances '
+                               '(bounded CPU sample)', 'n_fft': NFFT, 'win': WIN, 'hop': HOP},
+        'cpu_baseline': {'value': value, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from single_speaker_tts_b200 import _lib, _runtime
+    from single_speaker_tts_b200.audio import features as feat_api
+    from single_speaker_tts_b200.audio import synthesis
+    from single_speaker_tts_b200.synthetic import make_clips
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    peak_gbs, peak_src = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        """warmup untimed calls, then `steps` calls between barriers; CUDA-event time, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms)
+
+    # ---- workload: configs[1]/[2], 256 ragged clips per rank (weak scaling) ----
+    clips = make_clips(N_UTTS, seed=1 + rank, pool=16)
+    audio_in_s = sum(len(c) for c in clips) / SR
+    frames = [1 + len(c) // HOP for c in clips]
+    total_frames = sum(frames)
+    audio_out_s = sum(HOP * (t - 1) for t in frames) / SR
+
+    # magnitudes |STFT(clip)| produced on the device by our own feature kernel (float64 transform)
+    fb = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, want_spec=True, precision='f64',
+                                      keep_on_device=True)
+    mag_dev = fb.spec.abs().contiguous()                      # (sum T, 1025) float32, frame-major
+    del fb
+    mag_host = mag_dev.cpu().numpy()
+    foff = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+    mags_host = [mag_host[foff[i]:foff[i + 1]].T for i in range(N_UTTS)]   # (1025, T) views, like spec.T
+
+    # ---- device-resident Griffin-Lim through the C ABI ----
+    cfg = _runtime._make_config(NFFT, WIN, HOP, 'f32')
+    plan = ctypes.c_void_p()
+    _lib.check(lib.sstts_gl_plan_create(ctypes.byref(cfg), N_UTTS,
+                                        foff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(plan)))
+    ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan)), dtype=torch.uint8, device=dev)
+    n_samples = int(lib.sstts_gl_total_samples(plan))
+    wav_dev = torch.empty(n_samples, dtype=torch.float32, device=dev)
+    phase_dev = torch.empty((total_frames, N_BINS, 2), dtype=torch.float32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def gl_step(n_iter=GL_ITERS):
+        _lib.check(lib.sstts_random_phase(ctypes.c_uint64(1234), total_frames * N_BINS,
+                                          ctypes.c_void_p(phase_dev.data_ptr()), stream))
+        _lib.check(lib.sstts_griffin_lim(plan, ctypes.c_void_p(mag_dev.data_ptr()),
+                                         ctypes.c_void_p(phase_dev.data_ptr()), n_iter,
+                                         ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(wav_dev.data_ptr()),
+                                         None, stream))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    gl_ms = timed(gl_step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    total_audio = sum_over_ranks(audio_out_s)
+    gl_value = total_audio * args.steps / (gl_ms / 1000.0)
+
+    # dominant kernel (gl_step_kernel, 50 launches per step): average launch duration from the
+    # CUDA-event time of the full step minus the same call with n_iter = 0 (synth + finalize only)
+    base_ms = timed(lambda: gl_step(0), args.steps, 1)
+    iter_ms = max(1e-9, (gl_ms - base_ms) / (args.steps * GL_ITERS))
+    gl_alg_bytes = GL_BYTES_PER_FRAME_ITER * total_frames
+    gl_achieved = gl_alg_bytes / (iter_ms / 1000.0) / 1e9
+
+    # ---- e2e Griffin-Lim through the public API (host numpy in, host numpy out) ----
+    def gl_e2e():
+        synthesis.spectrograms_to_wavs(mags_host, WIN, HOP, NFFT, GL_ITERS, seed=1234)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    gl_e2e_ms = timed(gl_e2e, e2e_steps, 1)
+    gl_e2e_value = total_audio * e2e_steps / (gl_e2e_ms / 1000.0)
+    h2d = total_frames * N_BINS * 4
+    d2h = n_samples * 4
+
+    # ---- feature pipeline (configs[1]) ----
+    consts = (35.66, 100.0, 6.02, 99.89)
+    feat = {}
+    for prec in ('f64', 'f32'):
+        fcfg = _runtime._make_config(NFFT, WIN, HOP, prec, SR, 80, 0, 8000)
+        fplan = ctypes.c_void_p()
+        soff = np.concatenate([[0], np.cumsum([len(c) for c in clips])]).astype(np.int64)
+        _lib.check(lib.sstts_feat_plan_create(ctypes.byref(fcfg), N_UTTS,
+                                              soff.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 5,
+                                              ctypes.byref(fplan)))
+        rows = int(lib.sstts_feat_total_rows(fplan))
+        wav_in = torch.from_numpy(np.concatenate(clips)).to(dev)
+        lin = torch.empty((rows, N_BINS), dtype=torch.float32, device=dev)
+        mel = torch.empty((rows, 80), dtype=torch.float32, device=dev)
+        out = _lib.FeatOutputs()
+        out.lin_db_dev, out.mel_db_dev = lin.data_ptr(), mel.data_ptr()
+        out.normalize = 1
+        out.lin_ref_db, out.lin_max_db, out.mel_ref_db, out.mel_max_db = consts
+        out.mel_power = 1.0
+
+        def feat_step():
+            _lib.check(lib.sstts_stft_features(fplan, ctypes.c_void_p(wav_in.data_ptr()), ctypes.byref(out), stream))
+
+        f_ms = timed(feat_step, args.steps * 5, args.warmup)
+        per_launch_ms = f_ms / (args.steps * 5)
+        alg = 4 * int(soff[-1]) + FEAT_BYTES_PER_FRAME * total_frames
+        feat[prec] = {
+            'value': sum_over_ranks(audio_in_s) / (per_launch_ms / 1000.0), 'unit': 'audio-s/s',
+            'ms_per_step': per_launch_ms,
+            'roofline': {'bound': 'hbm', 'achieved': alg / (per_launch_ms / 1000.0) / 1e9, 'peak': peak_gbs,
+                         'unit': 'GB/s', 'frac': alg / (per_launch_ms / 1000.0) / 1e9 / peak_gbs, 'traffic': None},
+        }
+        lib.sstts_feat_plan_destroy(fplan)
+        del lin, mel, wav_in
+
+    def feat_e2e():
+        feat_api.features_batch(clips, NFFT, HOP, WIN, SR, 80, 0, 8000, *consts, reduction=5)
+
+    f_e2e_ms = timed(feat_e2e, e2e_steps, 1)
+    rows5 = sum(-(-t // 5) * 5 for t in frames)
+    feat_e2e = {'value': sum_over_ranks(audio_in_s) * e2e_steps / (f_e2e_ms / 1000.0), 'unit': 'audio-s/s',
+                'h2d_bytes_per_step': int(sum(len(c) for c in clips)) * 4,
+                'd2h_bytes_per_step': rows5 * (N_BINS + 80) * 4}
+
+    # ---- CPU baseline on rank 0 (oracle, bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0))
+        use = min(6, cores)                   # tacotron/params/inference.py:34: 6 synthesis workers
+        mags = oracle_sample(use, 3.0, seed=2)
+        with mp.get_context('fork').Pool(use) as pool:
+            a, dt = time_oracle_gl(pool, mags, 1000)
+        cpu = {'value': a / dt, 'unit': 'audio-s/s', 'cores': use, 'kind': 'port',
+               'sample': '{} utterances x 3 s, {} iterations, pool of {} processes (host has {} cores)'.format(
+                   use, GL_ITERS, use, cores)}
+
+    lib.sstts_gl_plan_destroy(plan)
+    if rank == 0:
+        line = {
+            'metric': 'griffin_lim_50it_audio_sec_per_sec', 'value': gl_value, 'unit': 'audio-s/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': gl_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[2]: Griffin-Lim 50 it over 256 ragged synthetic utterances '
+                                   '(1-10 s, 22.05 kHz) per GPU', 'n_fft': NFFT, 'win': WIN, 'hop': HOP,
+                       'n_utterances_per_gpu': N_UTTS, 'frames_per_gpu': total_frames,
+                       'audio_seconds_per_gpu': audio_out_s, 'l2': 'inputs_exceed_l2 (|S| 4.1 KB/frame + '
+                       'waveform state >> 126 MB)', 'sharding': 'by utterance, no collective'},
+            'e2e': {'value': gl_e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': gl_e2e_ms / e2e_steps},
+            'gpu_launches': args.steps * (GL_ITERS + 3),
+            'roofline': {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+                         'frac': gl_achieved / peak_gbs, 'traffic': None, 'kernel': 'gl_step_kernel',
+                         'peak_source': peak_src, 'ms_per_launch': iter_ms,
+                         'algorithmic_bytes_per_launch': gl_alg_bytes,
+                         'how': '(CUDA-event time of the 50-iteration call - same call with 0 iterations) / 50'},
+            'cpu_baseline': cpu,
+            'clocks': clocks,
+            'features': {'metric': 'feature_audio_sec_per_sec',
+                         'workload': 'BASELINE configs[1]: STFT -> linear + 80-mel dB-normalised features, '
+                                     '256 ragged clips per GPU',
+                         'f64': feat['f64'], 'f32_fast': feat['f32'], 'e2e': feat_e2e,
+                         'dtype': 'f64 (default; f32_fast is the opt-in float32 transform)'},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,319 @@
+"""Host-side batch engines over libsstts: packing of ragged batches, device buffers, streams.
+
+PyTorch is used for plumbing only (pinned/device allocations, streams, NCCL); the arithmetic
+is done by the CUDA kernels behind the C ABI (``include/sstts.h``).  Nothing here falls back to
+the CPU: without the built library or without a CUDA device the calls raise.
+"""
+import collections
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SsttsError
+
+_PRECISIONS = {'f32': _lib.SSTTS_F32, 'f64': _lib.SSTTS_F64,
+               'float32': _lib.SSTTS_F32, 'float64': _lib.SSTTS_F64}
+
+
+def require_cuda(device=None):
+    """Return the torch CUDA device to run on; raise if there is none (no CPU fallback)."""
+    if not torch.cuda.is_available():
+        raise SsttsError('single_speaker_tts_b200 needs a CUDA device (B200, sm_100a); '
+                         'there is no CPU fallback.')
+    if device is None:
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _make_config(n_fft, win_length, hop_length, precision, sampling_rate=0, n_mels=0, fmin=0.0,
+                 fmax=None):
+    cfg = _lib.StftConfig()
+    cfg.n_fft = int(n_fft)
+    cfg.win_length = int(win_length)
+    cfg.hop_length = int(hop_length)
+    cfg.sampling_rate = int(sampling_rate or 0)
+    cfg.n_mels = int(n_mels or 0)
+    cfg.mel_fmin = float(fmin or 0.0)
+    cfg.mel_fmax = float(fmax) if fmax else 0.0
+    cfg.precision = _PRECISIONS[precision]
+    return cfg
+
+
+class _Plan:
+    """Owns one native plan handle; destroyed with the object."""
+
+    def __init__(self, handle, destroy):
+        self.handle = handle
+        self._destroy = destroy
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _PlanCache:
+    """Small thread-safe LRU of native plans keyed by geometry + batch shape + device."""
+
+    def __init__(self, capacity=8):
+        self._cap = capacity
+        self._d = collections.OrderedDict()
+        self._lock = threading.Lock()
+
+    def get(self, key, factory):
+        with self._lock:
+            plan = self._d.get(key)
+            if plan is not None:
+                self._d.move_to_end(key)
+                return plan
+        plan = factory()
+        with self._lock:
+            self._d[key] = plan
+            while len(self._d) > self._cap:
+                self._d.popitem(last=False)
+        return plan
+
+
+_gl_plans = _PlanCache()
+_feat_plans = _PlanCache()
+
+
+def _offsets(counts):
+    off = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(counts, dtype=np.int64), out=off[1:])
+    return off
+
+
+def _pack_rows_pinned(blocks, width, dtype):
+    """Stack 2-D blocks (rows_i, width) into one pinned host tensor (sum rows, width)."""
+    rows = sum(b.shape[0] for b in blocks)
+    host = torch.empty((rows, width), dtype=dtype, pin_memory=True)
+    dst = host.numpy()
+    r = 0
+    for b in blocks:
+        n = b.shape[0]
+        np.copyto(dst[r:r + n], b, casting='unsafe')
+        r += n
+    return host
+
+
+# ----------------------------------------------------------------------------------------------
+# Griffin-Lim
+# ----------------------------------------------------------------------------------------------
+def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
+                      precision='f32', return_mse=False, device=None):
+    """Griffin-Lim for a ragged batch (reference: audio/synthesis.py:43-125, one call per item).
+
+    mags   : list of (1 + n_fft/2, T_i) magnitude spectrograms (any float dtype / layout).
+    angles : optional list of complex (1 + n_fft/2, T_i) initial unit phasors (the reference's
+             ``np.exp(2j*pi*np.random.rand(...))``); if None they are generated on the device from
+             ``seed`` (seed=None draws one 63-bit seed from numpy's global RNG, so
+             ``np.random.seed`` still makes a run reproducible).
+    Returns (list of float32 waveforms of length hop*(T_i-1), list of mse floats or None).
+    """
+    lib = _lib.load()
+    dev = require_cuda(device)
+    n_bins = 1 + n_fft // 2
+    n = len(mags)
+    if n == 0:
+        return [], ([] if return_mse else None)
+    frames = []
+    for m in mags:
+        if m.ndim != 2 or m.shape[0] != n_bins:
+            raise ValueError('spectrogram must have shape ({}, T), got {}'.format(n_bins, m.shape))
+        if m.shape[1] < 1:
+            raise ValueError('spectrogram needs at least one frame')
+        frames.append(m.shape[1])
+    if return_mse and n_iter < 1:
+        raise ValueError('mse needs n_iter >= 1')
+    frame_off = _offsets(frames)
+    cfg = _make_config(n_fft, win_length, hop_length, precision)
+    key = (dev.index, n_fft, win_length, hop_length, cfg.precision, frame_off.tobytes())
+
+    def factory():
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.sstts_gl_plan_create(ctypes.byref(cfg), n,
+                                                frame_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                ctypes.byref(h)))
+        return _Plan(h, lib.sstts_gl_plan_destroy)
+
+    plan = _gl_plans.get(key, factory)
+    total_frames = int(frame_off[-1])
+    total_samples = int(lib.sstts_gl_total_samples(plan.handle))
+    sample_off = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(n + 1,)).copy()
+
+    with torch.cuda.device(dev):
+        mag_host = _pack_rows_pinned([m.T for m in mags], n_bins, torch.float32)
+        mag_dev = mag_host.to(dev, non_blocking=True)
+        if angles is not None:
+            if len(angles) != n:
+                raise ValueError('need one initial phase array per spectrogram')
+            blocks = []
+            for a, m in zip(angles, mags):
+                if a.shape != m.shape:
+                    raise ValueError('initial phase shape {} != spectrogram shape {}'.format(a.shape, m.shape))
+                blocks.append(np.asarray(a).T)
+            ph_host = _pack_rows_pinned(blocks, n_bins, torch.complex64)
+            phase_dev = torch.view_as_real(ph_host.to(dev, non_blocking=True))
+        else:
+            if seed is None:
+                seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
+            phase_dev = torch.empty((total_frames, n_bins, 2), dtype=torch.float32, device=dev)
+            _lib.check(lib.sstts_random_phase(ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                              total_frames * n_bins, _ptr(phase_dev), _stream_ptr()))
+        ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan.handle)), dtype=torch.uint8, device=dev)
+        wav_dev = torch.empty(max(total_samples, 1), dtype=torch.float32, device=dev)
+        mse_dev = torch.zeros(total_frames, dtype=torch.float64, device=dev) if return_mse else None
+        _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
+                                         _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
+        wav_host = torch.empty(max(total_samples, 1), dtype=torch.float32, pin_memory=True)
+        wav_host.copy_(wav_dev, non_blocking=True)
+        mse_host = mse_dev.cpu() if return_mse else None
+        torch.cuda.current_stream().synchronize()
+    wav_np = wav_host.numpy()
+    wavs = [wav_np[sample_off[i]:sample_off[i + 1]] for i in range(n)]
+    mses = None
+    if return_mse:
+        mf = mse_host.numpy()
+        mses = []
+        for i in range(n):
+            if frames[i] < 2:
+                mses.append(None)
+            else:
+                mses.append(float(mf[frame_off[i]:frame_off[i + 1]].sum() / (n_bins * frames[i])))
+    return wavs, mses
+
+
+# ----------------------------------------------------------------------------------------------
+# STFT features
+# ----------------------------------------------------------------------------------------------
+class FeatureBatch:
+    """Result of :func:`stft_features_batch` (host arrays, split per clip on access)."""
+
+    def __init__(self, n_clips, frames, row_off, reduction):
+        self.n_clips = n_clips
+        self.frames = frames
+        self.row_off = row_off
+        self.reduction = reduction
+        self.spec = None      # (rows, bins) complex64
+        self.lin_db = None    # (rows, bins) float32
+        self.mel_db = None    # (rows, n_mels) float32
+        self.mel_raw = None   # (rows, n_mels) float64
+        self.minmax = None    # (n_clips, 4) float64
+        self.mel_basis = None
+
+    def rows(self, arr, i, padded=False):
+        a, b = int(self.row_off[i]), int(self.row_off[i + 1])
+        if not padded:
+            b = a + self.frames[i]
+        return arr[a:b]
+
+
+def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None, n_mels=0, fmin=0.0,
+                        fmax=None, reduction=1, want_spec=False, want_lin=False, want_mel=False,
+                        want_mel_raw=False, want_minmax=False, normalize=None, power=1.0,
+                        precision='f64', device=None, keep_on_device=False):
+    """Batched STFT -> |.| -> linear / mel -> dB -> (0,1) pipeline on the GPU.
+
+    normalize: None (raw dB) or (lin_ref_db, lin_max_db, mel_ref_db, mel_max_db) as in
+    audio/conversion.py:56-78.  Outputs are frame-major (rows, bins); with ``reduction`` r > 1 every
+    clip's rows are zero-padded to a multiple of r (datasets/dataset_helper.py:357-401).
+    """
+    lib = _lib.load()
+    dev = require_cuda(device)
+    n_bins = 1 + n_fft // 2
+    n = len(wavs)
+    if n == 0:
+        raise ValueError('empty batch')
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    lens = []
+    for w in wavs:
+        if w.ndim != 1:
+            raise ValueError('Invalid shape for monophonic audio: ndim={:d}'.format(w.ndim))
+        if w.shape[0] < 1:
+            raise ValueError('clip is empty')
+        lens.append(w.shape[0])
+    sample_off = _offsets(lens)
+    need_mel = want_mel or want_mel_raw or want_minmax
+    cfg = _make_config(n_fft, win_length, hop_length, precision, sampling_rate if need_mel else 0,
+                       n_mels if need_mel else 0, fmin, fmax)
+    key = (dev.index, n_fft, win_length, hop_length, cfg.precision, cfg.sampling_rate, cfg.n_mels,
+           cfg.mel_fmin, cfg.mel_fmax, int(reduction), sample_off.tobytes())
+
+    def factory():
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.sstts_feat_plan_create(ctypes.byref(cfg), n,
+                                                  sample_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                  int(reduction), ctypes.byref(h)))
+        return _Plan(h, lib.sstts_feat_plan_destroy)
+
+    plan = _feat_plans.get(key, factory)
+    rows = int(lib.sstts_feat_total_rows(plan.handle))
+    frame_off = np.ctypeslib.as_array(lib.sstts_feat_frame_offsets(plan.handle), shape=(n + 1,)).copy()
+    row_off = np.ctypeslib.as_array(lib.sstts_feat_row_offsets(plan.handle), shape=(n + 1,)).copy()
+    res = FeatureBatch(n, [int(frame_off[i + 1] - frame_off[i]) for i in range(n)], row_off, reduction)
+    if need_mel and cfg.n_mels > 0:
+        res.mel_basis = np.ctypeslib.as_array(lib.sstts_feat_mel_basis(plan.handle),
+                                              shape=(cfg.n_mels, n_bins)).copy()
+
+    with torch.cuda.device(dev):
+        wav_host = torch.empty(int(sample_off[-1]), dtype=torch.float32, pin_memory=True)
+        dst = wav_host.numpy()
+        for i, w in enumerate(wavs):
+            np.copyto(dst[sample_off[i]:sample_off[i + 1]], w, casting='unsafe')
+        wav_dev = wav_host.to(dev, non_blocking=True)
+        out = _lib.FeatOutputs()
+        spec_dev = torch.empty((rows, n_bins, 2), dtype=torch.float32, device=dev) if want_spec else None
+        lin_dev = torch.empty((rows, n_bins), dtype=torch.float32, device=dev) if want_lin else None
+        mel_dev = torch.empty((rows, cfg.n_mels), dtype=torch.float32, device=dev) if want_mel else None
+        raw_dev = torch.empty((rows, cfg.n_mels), dtype=torch.float64, device=dev) if want_mel_raw else None
+        mm_dev = torch.empty((n, 4), dtype=torch.float64, device=dev) if want_minmax else None
+        out.spec_dev = spec_dev.data_ptr() if want_spec else None
+        out.lin_db_dev = lin_dev.data_ptr() if want_lin else None
+        out.mel_db_dev = mel_dev.data_ptr() if want_mel else None
+        out.mel_raw_dev = raw_dev.data_ptr() if want_mel_raw else None
+        out.minmax_dev = mm_dev.data_ptr() if want_minmax else None
+        out.normalize = 1 if normalize is not None else 0
+        if normalize is not None:
+            out.lin_ref_db, out.lin_max_db, out.mel_ref_db, out.mel_max_db = [float(v) for v in normalize]
+        out.mel_power = float(power)
+        _lib.check(lib.sstts_stft_features(plan.handle, _ptr(wav_dev), ctypes.byref(out), _stream_ptr()))
+        if keep_on_device:
+            res.spec = torch.view_as_complex(spec_dev) if want_spec else None
+            res.lin_db, res.mel_db, res.mel_raw, res.minmax = lin_dev, mel_dev, raw_dev, mm_dev
+            return res
+
+        def to_host(t):
+            if t is None:
+                return None
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+
+        spec_h, lin_h, mel_h, raw_h, mm_h = [to_host(t) for t in (spec_dev, lin_dev, mel_dev, raw_dev, mm_dev)]
+        torch.cuda.current_stream().synchronize()
+    res.spec = torch.view_as_complex(spec_h).numpy() if spec_h is not None else None
+    res.lin_db = lin_h.numpy() if lin_h is not None else None
+    res.mel_db = mel_h.numpy() if mel_h is not None else None
+    res.mel_raw = raw_h.numpy() if raw_h is not None else None
+    res.minmax = mm_h.numpy() if mm_h is not None else None
+    return res

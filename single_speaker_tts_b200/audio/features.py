@@ -1,0 +1,52 @@
+"""``audio/features.py`` of the reference, executed by the sm_100a STFT feature kernel.
+
+Signatures, argument order, defaults, output orientation ((bins, T)) and dtypes follow the
+reference (audio/features.py:5-6,116); the transform runs in float64 on the device by default so
+that every bin matches librosa's float64 ``stft`` (``precision='f32'`` selects the faster
+float32 transform, whose bins more than ~100 dB below the frame peak differ).
+"""
+import numpy as np
+
+from .. import _runtime
+
+
+def linear_scale_spectrogram(wav, n_fft, hop_length=None, win_length=None, precision='f64'):
+    """STFT -- reference audio/features.py:116-145.  (1 + n_fft/2, T) complex64, Fortran order."""
+    wav = np.asarray(wav)
+    res = _runtime.stft_features_batch([wav], n_fft, hop_length, win_length, want_spec=True,
+                                       precision=precision)
+    return res.spec.T
+
+
+def mel_scale_spectrogram(wav, n_fft, sampling_rate, n_mels, fmin, fmax, hop_length, win_length,
+                          power, precision='f64'):
+    """Mel spectrogram ``mel_basis @ |STFT| ** power`` -- reference audio/features.py:5-86.
+    (n_mels, T) float64."""
+    wav = np.asarray(wav)
+    res = _runtime.stft_features_batch([wav], n_fft, hop_length, win_length,
+                                       sampling_rate=sampling_rate, n_mels=n_mels, fmin=fmin,
+                                       fmax=fmax, want_mel_raw=True, power=power,
+                                       precision=precision)
+    return res.mel_raw.T
+
+
+def features_batch(wavs, n_fft, hop_length, win_length, sampling_rate, n_mels, fmin, fmax,
+                   linear_ref_db, linear_mag_max_db, mel_mag_ref_db, mel_mag_max_db, reduction=1,
+                   precision='f64'):
+    """Batched ``load_audio`` core (reference datasets/lj_speech.py:124-156 after decode/trim):
+    one STFT per clip, fused |.| -> dB -> normalise for the linear and the mel spectrogram,
+    reduction padding and folding.  Returns a list of ``(mel, lin)`` float32 pairs shaped
+    ``(ceil(T/r), r * n_mels)`` and ``(ceil(T/r), r * (1 + n_fft/2))``."""
+    res = _runtime.stft_features_batch(list(wavs), n_fft, hop_length, win_length,
+                                       sampling_rate=sampling_rate, n_mels=n_mels, fmin=fmin,
+                                       fmax=fmax, reduction=reduction, want_lin=True, want_mel=True,
+                                       normalize=(linear_ref_db, linear_mag_max_db, mel_mag_ref_db,
+                                                  mel_mag_max_db),
+                                       precision=precision)
+    out = []
+    n_bins = 1 + n_fft // 2
+    for i in range(res.n_clips):
+        mel = res.rows(res.mel_db, i, padded=True).reshape((-1, n_mels * reduction))
+        lin = res.rows(res.lin_db, i, padded=True).reshape((-1, n_bins * reduction))
+        out.append((mel, lin))
+    return out

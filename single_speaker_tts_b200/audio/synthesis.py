@@ -1,0 +1,58 @@
+"""``audio/synthesis.py`` of the reference, executed by the sm_100a Griffin-Lim kernels.
+
+``spectrogram_to_wav`` / ``griffin_lim_v2`` keep the reference signatures (audio/synthesis.py:5,43)
+including the use of numpy's GLOBAL random state for the initial phase (:85), so
+``np.random.seed(s)`` before a call selects the same initial phase as in the reference.
+``spectrograms_to_wavs`` is the batched entry point that replaces the 6-worker pool of
+``tacotron/inference.py:185-188`` / ``tacotron/serve.py:69-72``.
+"""
+import numpy as np
+
+from .. import _runtime
+
+
+def _initial_angles(shape):
+    # reference audio/synthesis.py:85
+    return np.exp(2j * np.pi * np.random.rand(*shape))
+
+
+def griffin_lim_v2(spectrogram, win_length, hop_length, n_fft, n_iter, angles=None,
+                   precision='f32'):
+    """Griffin-Lim reconstruction -- reference audio/synthesis.py:43-125.
+
+    Returns ``(audio float32 of length hop*(T-1), mse)``; ``mse`` is the mean squared magnitude
+    error of the last iteration (None when ``n_iter`` == 0, like the reference).
+    ``angles`` (extension) overrides the random initial phase.
+    """
+    spectrogram = np.asarray(spectrogram)
+    if angles is None:
+        angles = _initial_angles(spectrogram.shape)
+    wavs, mses = _runtime.griffin_lim_batch([spectrogram], win_length, hop_length, n_fft, n_iter,
+                                            angles=[angles], precision=precision,
+                                            return_mse=n_iter > 0)
+    return wavs[0], (mses[0] if mses is not None else None)
+
+
+def spectrogram_to_wav(mag, win_length, hop_length, n_fft, n_iter, angles=None, precision='f32'):
+    """Magnitude spectrogram -> float32 waveform -- reference audio/synthesis.py:5-40."""
+    mag = np.asarray(mag)
+    if angles is None:
+        angles = _initial_angles(mag.shape)
+    wavs, _ = _runtime.griffin_lim_batch([mag], win_length, hop_length, n_fft, n_iter,
+                                         angles=[angles], precision=precision)
+    return wavs[0].astype(np.float32)
+
+
+def spectrograms_to_wavs(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
+                         precision='f32', return_mse=False):
+    """Batched Griffin-Lim over a ragged list of (1 + n_fft/2, T_i) magnitude spectrograms.
+
+    One device call for the whole batch (utterances packed with an offsets table).  ``angles`` is
+    an optional list of initial phasors (one per item); otherwise the phase is generated on the
+    device from ``seed`` (None: one seed is drawn from numpy's global RNG).
+    Returns a list of float32 waveforms (and the list of last-iteration mse values if requested).
+    """
+    wavs, mses = _runtime.griffin_lim_batch(list(mags), win_length, hop_length, n_fft, n_iter,
+                                            angles=angles, seed=seed, precision=precision,
+                                            return_mse=return_mse)
+    return (wavs, mses) if return_mse else wavs

@@ -92,10 +92,11 @@ struct FeatPlanHost {
   long long total_frames = 0, total_rows = 0;
 };
 
-inline bool build_feat_plan(int n_clips, const long long* sample_off, int win, int hop, int reduction,
-                            FeatPlanHost& P, std::string& err) {
-  if (win < 2 || win > NFFT || hop < 1) { err = "need hop >= 1 and 2 <= win <= n_fft"; return false; }
-  if ((NFFT - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
+inline bool build_feat_plan(int n_clips, const long long* sample_off, int n_fft, int win, int hop,
+                            int reduction, FeatPlanHost& P, std::string& err) {
+  if (n_fft != 2048 && n_fft != 1024 && n_fft != 512) { err = "n_fft must be 2048, 1024 or 512"; return false; }
+  if (win < 2 || win > n_fft || hop < 1) { err = "need hop >= 1 and 2 <= win <= n_fft"; return false; }
+  if ((n_fft - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
   if (reduction < 1) reduction = 1;
   P.n_clips = n_clips; P.win = win; P.hop = hop; P.reduction = reduction;
   P.sample_off.assign(sample_off, sample_off + n_clips + 1);

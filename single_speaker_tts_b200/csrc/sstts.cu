@@ -83,10 +83,15 @@ StftTables<T> tables_view(const DeviceTables& D) {
   return t;
 }
 
-int check_config(const sstts_stft_config* cfg) {
+int check_config(const sstts_stft_config* cfg, bool allow_embedded) {
   if (!cfg) return fail(SSTTS_ERR_INVALID, "config is NULL");
-  if (cfg->n_fft != NFFT) return fail(SSTTS_ERR_INVALID, "only n_fft = 2048 is built");
-  if (cfg->win_length < 2 || cfg->win_length > NFFT || ((NFFT - cfg->win_length) & 1))
+  if (allow_embedded) {
+    if (cfg->n_fft != 2048 && cfg->n_fft != 1024 && cfg->n_fft != 512)
+      return fail(SSTTS_ERR_INVALID, "features: n_fft must be 2048, 1024 or 512");
+  } else if (cfg->n_fft != NFFT) {
+    return fail(SSTTS_ERR_INVALID, "griffin_lim: only n_fft = 2048 is built");
+  }
+  if (cfg->win_length < 2 || cfg->win_length > cfg->n_fft || ((cfg->n_fft - cfg->win_length) & 1))
     return fail(SSTTS_ERR_INVALID, "win_length must be in [2, n_fft] with n_fft - win_length even");
   if (cfg->hop_length < 1) return fail(SSTTS_ERR_INVALID, "hop_length must be >= 1");
   if (cfg->precision != SSTTS_F32 && cfg->precision != SSTTS_F64)
@@ -94,8 +99,10 @@ int check_config(const sstts_stft_config* cfg) {
   return 0;
 }
 
-bool is_model_geometry(int win, int hop) { return win == 1102 && hop == 275; }
-typedef StaticGeom<1102, 275> ModelGeom;
+bool is_model_geometry(int n_fft, int win, int hop) { return n_fft == 2048 && win == 1102 && hop == 275; }
+bool is_stats_geometry(int n_fft, int win, int hop) { return n_fft == 1024 && win == 1024 && hop == 256; }
+typedef StaticGeom<1102, 275, 2048> ModelGeom;   // tacotron/params/model.py:13-24
+typedef StaticGeom<1024, 256, 1024> StatsGeom;   // datasets/statistics.py:31-34
 
 int sm_count() {
   int dev = 0, n = 0;
@@ -165,7 +172,7 @@ int sstts_device_count(void) {
 int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t* frame_off_host,
                          sstts_gl_plan** plan_out) {
   if (plan_out) *plan_out = nullptr;
-  int rc = check_config(cfg);
+  int rc = check_config(cfg, false);
   if (rc) return rc;
   if (!plan_out || !frame_off_host || n_utts < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
   sstts_gl_plan* P = new (std::nothrow) sstts_gl_plan();
@@ -321,6 +328,7 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   A.mel_power = (float)(O->mel_power == 0.0 ? 1.0 : O->mel_power);
   A.normalize = O->normalize;
   A.win = H.win; A.hop = H.hop; A.span_max = H.span_max;
+  A.n_fft = P->cfg.n_fft;
   if (A.n_mels < 1) { A.mel_out = nullptr; A.melraw_out = nullptr; }
 
   const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max);
@@ -356,7 +364,7 @@ int sstts_griffin_lim(const sstts_gl_plan* P, const float* mag_dev, const float*
   if (P->host.total_samples > 0 && !wav_out_dev) return fail(SSTTS_ERR_INVALID, "wav_out_dev is NULL");
   if (mse_frame_dev && n_iter < 1) return fail(SSTTS_ERR_INVALID, "mse needs n_iter >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool model = is_model_geometry(P->host.win, P->host.hop);
+  const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   if (P->cfg.precision == SSTTS_F64) {
     return model ? run_griffin_lim<double, ModelGeom, 4>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
                                                          wav_out_dev, mse_frame_dev, st)
@@ -384,7 +392,7 @@ int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream)
 int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int64_t* sample_off_host,
                            int reduction, sstts_feat_plan** plan_out) {
   if (plan_out) *plan_out = nullptr;
-  int rc = check_config(cfg);
+  int rc = check_config(cfg, true);
   if (rc) return rc;
   if (!plan_out || !sample_off_host || n_clips < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
   if (cfg->n_mels < 0 || cfg->n_mels > 1024) return fail(SSTTS_ERR_INVALID, "n_mels out of range");
@@ -393,7 +401,7 @@ int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int6
   P->cfg = *cfg;
   std::string err;
   std::vector<long long> so(sample_off_host, sample_off_host + n_clips + 1);
-  if (!build_feat_plan(n_clips, so.data(), cfg->win_length, cfg->hop_length, reduction, P->host, err)) {
+  if (!build_feat_plan(n_clips, so.data(), cfg->n_fft, cfg->win_length, cfg->hop_length, reduction, P->host, err)) {
     delete P;
     return fail(SSTTS_ERR_INVALID, err);
   }
@@ -448,12 +456,16 @@ int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const ss
   if ((out->mel_db_dev || out->mel_raw_dev) && P->cfg.n_mels < 1)
     return fail(SSTTS_ERR_INVALID, "mel outputs requested but the plan has no filterbank");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool model = is_model_geometry(P->host.win, P->host.hop);
-  if (P->cfg.precision == SSTTS_F64)
-    return model ? run_features<double, ModelGeom, 4>(P, wav_dev, out, st)
-                 : run_features<double, DynGeom, 4>(P, wav_dev, out, st);
-  return model ? run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st)
-               : run_features<float, DynGeom, kWarps>(P, wav_dev, out, st);
+  const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
+  const bool stats = is_stats_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
+  if (P->cfg.precision == SSTTS_F64) {
+    if (model) return run_features<double, ModelGeom, 4>(P, wav_dev, out, st);
+    if (stats) return run_features<double, StatsGeom, 4>(P, wav_dev, out, st);
+    return run_features<double, DynGeom, 4>(P, wav_dev, out, st);
+  }
+  if (model) return run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st);
+  if (stats) return run_features<float, StatsGeom, kWarps>(P, wav_dev, out, st);
+  return run_features<float, DynGeom, kWarps>(P, wav_dev, out, st);
 }
 
 }  // extern "C"

@@ -39,18 +39,27 @@ constexpr int NBINS = HALF + 1;    // 1025
 // ---------------------------------------------------------------------------------------------
 // geometry policies: compile-time (win, hop) for the model configuration, run-time otherwise
 // ---------------------------------------------------------------------------------------------
-template <int WIN, int HOP> struct StaticGeom {
-  SSTTS_HD StaticGeom(int, int) {}
+// NFFT_EFF < 2048 embeds a shorter transform in the 2048-point one: the frame occupies the first
+// NFFT_EFF samples of the zero-padded buffer and only every (2048 / NFFT_EFF)-th bin is kept
+// (zero padding in time interpolates the spectrum, so those bins ARE the NFFT_EFF-point DFT).
+template <int WIN, int HOP, int NFFT_EFF = 2048> struct StaticGeom {
+  SSTTS_HD StaticGeom(int, int, int) {}
   SSTTS_HD constexpr int win() const { return WIN; }
   SSTTS_HD constexpr int hop() const { return HOP; }
-  SSTTS_HD constexpr int lpad() const { return (NFFT - WIN) / 2; }
+  SSTTS_HD constexpr int nfft() const { return NFFT_EFF; }
+  SSTTS_HD constexpr int lpad() const { return (NFFT_EFF - WIN) / 2; }   // window offset in the frame
+  SSTTS_HD constexpr int cpad() const { return NFFT_EFF / 2; }           // centre (reflect) padding
+  SSTTS_HD constexpr int bin_shift() const { return NFFT_EFF == 2048 ? 0 : NFFT_EFF == 1024 ? 1 : 2; }
 };
 struct DynGeom {
-  int win_, hop_;
-  SSTTS_HD DynGeom(int w, int h) : win_(w), hop_(h) {}
+  int win_, hop_, nfft_;
+  SSTTS_HD DynGeom(int w, int h, int n) : win_(w), hop_(h), nfft_(n) {}
   SSTTS_HD int win() const { return win_; }
   SSTTS_HD int hop() const { return hop_; }
-  SSTTS_HD int lpad() const { return (NFFT - win_) / 2; }
+  SSTTS_HD int nfft() const { return nfft_; }
+  SSTTS_HD int lpad() const { return (nfft_ - win_) / 2; }
+  SSTTS_HD int cpad() const { return nfft_ / 2; }
+  SSTTS_HD int bin_shift() const { return nfft_ == 2048 ? 0 : nfft_ == 1024 ? 1 : 2; }
 };
 
 // numpy.pad(mode='reflect') index map for any q (multi-bounce for short signals).
@@ -221,7 +230,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ m
 template <typename T, typename G, int W, bool FROM_PHASE>
 __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   typedef typename cx_of<T>::type C;
-  const G g(A.win, A.hop);
+  const G g(A.win, A.hop, NFFT);
   const int win = g.win(), hop = g.hop(), lpad = g.lpad();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = W * 32;
@@ -350,7 +359,7 @@ template <typename T> struct GLFinalArgs {
 
 template <typename T, typename G, int NT>
 __global__ void __launch_bounds__(NT) gl_finalize_kernel(const GLFinalArgs<T> A) {
-  const G g(A.win, A.hop);
+  const G g(A.win, A.hop, NFFT);
   const int win = g.win(), hop = g.hop(), lpad = g.lpad();
   const int tid = threadIdx.x;
   SSTTS_DYN_SMEM(smem);
@@ -410,6 +419,7 @@ template <typename T> struct FeatArgs {
   float mel_power;
   int normalize;
   int win, hop, span_max;
+  int n_fft;                      // effective transform size: 2048, 1024 or 512
 };
 
 SSTTS_D long long encode_ordered(double v) {
@@ -440,8 +450,10 @@ template <> struct feat_math<double> {
 template <typename T, typename G, int W>
 __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> A) {
   typedef typename cx_of<T>::type C;
-  const G g(A.win, A.hop);
-  const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const G g(A.win, A.hop, A.n_fft);
+  const int win = g.win(), hop = g.hop(), lpad = g.lpad(), cpad = g.cpad();
+  const int bshift = g.bin_shift(), bmask = (1 << bshift) - 1;
+  const int n_bins = (HALF >> bshift) + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = W * 32;
 
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
     const float* x = A.wav + soff;
 
     for (int s = tid; s < span; s += NT) {
-      int q = span_lo + s - HALF;
+      int q = span_lo + s - cpad;
       if (q < 0 || q >= n_samples) q = reflect_index(q, n_samples);
       s_x[s] = x[q];
     }
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
     if (tl.last && n_rows > n_frames) {
       const long long zr0 = r0 + n_frames;
       const int nz = n_rows - n_frames;
-      if (A.lin_out) for (int i = tid; i < nz * NBINS; i += NT) A.lin_out[zr0 * NBINS + i] = 0.0f;
+      if (A.lin_out) for (int i = tid; i < nz * n_bins; i += NT) A.lin_out[zr0 * n_bins + i] = 0.0f;
       if (A.mel_out) for (int i = tid; i < nz * A.n_mels; i += NT) A.mel_out[zr0 * A.n_mels + i] = 0.0f;
     }
     __syncthreads();
@@ -522,21 +534,24 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
         const T woi = w.y * di - w.x * dr;
         const T xkr = T(0.5) * (er + wor), xki = T(0.5) * (ei + woi);   // X[k]
         const T xnr = T(0.5) * (er - wor), xni = T(0.5) * (woi - ei);   // X[N-k]
-        if (A.spec_out) {
-          A.spec_out[row * NBINS + k] = make_float2((float)xkr, (float)xki);
-          A.spec_out[row * NBINS + kn] = make_float2((float)xnr, (float)xni);
+        if ((k & bmask) == 0) {   // kn = 1024 - k shares k's residue
+          if (A.spec_out) {
+            A.spec_out[row * n_bins + (k >> bshift)] = make_float2((float)xkr, (float)xki);
+            A.spec_out[row * n_bins + (kn >> bshift)] = make_float2((float)xnr, (float)xni);
+          }
+          s_mag[k >> bshift] = feat_math<T>::magnitude(xkr, xki);
+          s_mag[kn >> bshift] = feat_math<T>::magnitude(xnr, xni);
         }
-        s_mag[k] = feat_math<T>::magnitude(xkr, xki);
-        s_mag[kn] = feat_math<T>::magnitude(xnr, xni);
       }
       if (lane == 0) {
         const int sl = brev5(16);
-        if (A.spec_out) A.spec_out[row * NBINS + HALF / 2] = make_float2((float)re[sl], (float)(-im[sl]));
-        s_mag[HALF / 2] = feat_math<T>::magnitude(re[sl], -im[sl]);
+        const int kh = (HALF / 2) >> bshift;
+        if (A.spec_out) A.spec_out[row * n_bins + kh] = make_float2((float)re[sl], (float)(-im[sl]));
+        s_mag[kh] = feat_math<T>::magnitude(re[sl], -im[sl]);
       }
       __syncwarp();
       if (want_lin || A.minmax_out) {
-        for (int k = lane; k < NBINS; k += 32) {
+        for (int k = lane; k < n_bins; k += 32) {
           const float db = 20.0f * log10f(fmaxf(1e-5f, s_mag[k]));
           mn_lin = fmin(mn_lin, (double)db);
           mx_lin = fmax(mx_lin, (double)db);
@@ -546,7 +561,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
               v = 1.0f + (db - A.lin_ref_db) / A.lin_range_db;
               v = fminf(fmaxf(v, 0.0f), 1.0f);
             }
-            A.lin_out[row * NBINS + k] = v;
+            A.lin_out[row * n_bins + k] = v;
           }
         }
       }

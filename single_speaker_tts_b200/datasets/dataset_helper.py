@@ -1,0 +1,79 @@
+"""Audio part of ``datasets/dataset_helper.py`` and ``datasets/lj_speech.py`` of the reference.
+
+Only the feature side is restated (``load_audio``, ``apply_reduction_padding``,
+``pre_compute_features``); the text side (vocabulary, sentence ids) is host string processing that
+stays with the reference's own code.
+"""
+import os
+
+import numpy as np
+
+from ..audio.conversion import ms_to_samples
+from ..audio.effects import trim
+from ..audio.features import features_batch
+from ..audio.io import load_wav
+from ..params import model_params
+
+
+class DatasetHelper:
+    """Feature recipe shared by the corpus loaders.  Subclasses provide the four dB constants."""
+    mel_mag_ref_db = None
+    mel_mag_max_db = None
+    linear_ref_db = None
+    linear_mag_max_db = None
+
+    @staticmethod
+    def apply_reduction_padding(mel_mag_db, linear_mag_db, reduction_factor):
+        """reference datasets/dataset_helper.py:357-401: zero-pad frames to a multiple of r, fold."""
+        n_frames = mel_mag_db.shape[0]
+        if (n_frames % reduction_factor) != 0:
+            n_padding_frames = reduction_factor - (n_frames % reduction_factor)
+            mel_mag_db = np.pad(mel_mag_db, [[0, n_padding_frames], [0, 0]], mode="constant")
+            linear_mag_db = np.pad(linear_mag_db, [[0, n_padding_frames], [0, 0]], mode="constant")
+        mel_mag_db = mel_mag_db.reshape((-1, mel_mag_db.shape[1] * reduction_factor))
+        linear_mag_db = linear_mag_db.reshape((-1, linear_mag_db.shape[1] * reduction_factor))
+        return mel_mag_db, linear_mag_db
+
+    @classmethod
+    def features_from_wavs(cls, wavs, sampling_rate=None, trim_silence=True, precision='f64'):
+        """Batched core of ``load_audio`` (reference datasets/lj_speech.py:119-156) for decoded
+        clips: trim -> one STFT -> linear + mel dB, normalised with the class constants ->
+        reduction padding -> float32.  Returns a list of ``(mel, lin)``."""
+        sr = sampling_rate or model_params.sampling_rate
+        win_len = ms_to_samples(model_params.win_len, model_params.sampling_rate)
+        hop_len = ms_to_samples(model_params.win_hop, model_params.sampling_rate)
+        if trim_silence:
+            wavs = [trim(w)[0] for w in wavs]
+        return features_batch(wavs, model_params.n_fft, hop_len, win_len, sr, model_params.n_mels,
+                              model_params.mel_fmin, model_params.mel_fmax, cls.linear_ref_db,
+                              cls.linear_mag_max_db, cls.mel_mag_ref_db, cls.mel_mag_max_db,
+                              reduction=model_params.reduction, precision=precision)
+
+    @classmethod
+    def load_audio(cls, file_path):
+        """reference datasets/lj_speech.py:106-156 -- ``file_path`` is ``bytes`` (tf.py_func)."""
+        wav, sr = load_wav(file_path.decode())
+        return cls.features_from_wavs([wav], sampling_rate=sr)[0]
+
+    @classmethod
+    def pre_compute_features(cls, paths, batch_clips=256):
+        """reference datasets/dataset_helper.py:326-355 -- ``<name>.npz`` next to every wav with
+        keys ``mel_mag_db`` / ``linear_mag_db``; clips go to the device in batches."""
+        n_samples = len(paths)
+        print('Loaded {} dataset entries.'.format(n_samples))
+        for s in range(0, n_samples, batch_clips):
+            chunk = paths[s:s + batch_clips]
+            wavs, srs = zip(*[load_wav(p) for p in chunk])
+            feats = cls.features_from_wavs(list(wavs), sampling_rate=srs[0])
+            for wav_path, (mel_mag_db, linear_mag_db) in zip(chunk, feats):
+                out_path = '{}.npz'.format(os.path.splitext(wav_path)[0])
+                print('Writing: "{}"'.format(out_path))
+                np.savez(out_path, mel_mag_db=mel_mag_db, linear_mag_db=linear_mag_db)
+
+
+class LJSpeechDatasetHelper(DatasetHelper):
+    """dB constants of reference datasets/lj_speech.py:20-29."""
+    mel_mag_ref_db = 6.02
+    mel_mag_max_db = 99.89
+    linear_ref_db = 35.66
+    linear_mag_max_db = 100.0

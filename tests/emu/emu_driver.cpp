@@ -97,19 +97,19 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
 }
 
 template <typename T, typename G, int W>
-int emu_feat_run(int win, int hop, int sr, int n_mels, double fmin, double fmax, int n_clips,
+int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, double fmax, int n_clips,
                  const long long* sample_off, int reduction, const float* wav, float* spec, float* lin,
                  float* mel, double* melraw, double* minmax, int normalize, double lin_ref,
                  double lin_max, double mel_ref, double mel_max, double power, int grid_cap) {
   FeatPlanHost H;
   std::string err;
-  if (!build_feat_plan(n_clips, sample_off, win, hop, reduction, H, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
+  if (!build_feat_plan(n_clips, sample_off, n_fft, win, hop, reduction, H, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
   HostTables<T> tabs;
   fill_tables<T>(win, tabs);
   MelCSR M;
   std::vector<T> mw;
   if (n_mels > 0) {
-    make_mel_csr(sr, NFFT, n_mels, fmin, fmax > 0 ? fmax : sr / 2.0, M);
+    make_mel_csr(sr, n_fft, n_mels, fmin, fmax > 0 ? fmax : sr / 2.0, M);
     mw.assign(M.w.begin(), M.w.end());
   }
   std::vector<long long> mm(4 * (size_t)n_clips);
@@ -123,7 +123,7 @@ int emu_feat_run(int win, int hop, int sr, int n_mels, double fmin, double fmax,
   A.lin_ref_db = (float)lin_ref; A.lin_range_db = (float)(fabs(lin_ref) + fabs(lin_max));
   A.mel_ref_db = mel_ref; A.mel_range_db = fabs(mel_ref) + fabs(mel_max);
   A.mel_power = (float)power; A.normalize = normalize;
-  A.win = win; A.hop = hop; A.span_max = H.span_max;
+  A.win = win; A.hop = hop; A.span_max = H.span_max; A.n_fft = n_fft;
   if (minmax) for (size_t i = 0; i < mm.size(); ++i) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
   const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
@@ -168,15 +168,21 @@ int emu_griffin_lim(int win, int hop, int prec, int n_utts, const long long* fra
                : emu_gl_run<float, DynGeom, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap);
 }
 
-int emu_stft_features(int win, int hop, int prec, int sr, int n_mels, double fmin, double fmax, int n_clips,
+int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels, double fmin, double fmax, int n_clips,
                       const long long* sample_off, int reduction, const float* wav, float* spec, float* lin,
                       float* mel, double* melraw, double* minmax, int normalize, double lin_ref,
                       double lin_max, double mel_ref, double mel_max, double power, int grid_cap) {
-  const bool model = (win == 1102 && hop == 275);
-#define FEAT_ARGS win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap
-  if (prec == 1)
-    return model ? emu_feat_run<double, StaticGeom<1102, 275>, 4>(FEAT_ARGS) : emu_feat_run<double, DynGeom, 4>(FEAT_ARGS);
-  return model ? emu_feat_run<float, StaticGeom<1102, 275>, kWarps>(FEAT_ARGS) : emu_feat_run<float, DynGeom, kWarps>(FEAT_ARGS);
+  const bool model = (n_fft == 2048 && win == 1102 && hop == 275);
+  const bool stats = (n_fft == 1024 && win == 1024 && hop == 256);
+#define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap
+  if (prec == 1) {
+    if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, 4>(FEAT_ARGS);
+    if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, 4>(FEAT_ARGS);
+    return emu_feat_run<double, DynGeom, 4>(FEAT_ARGS);
+  }
+  if (model) return emu_feat_run<float, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
+  if (stats) return emu_feat_run<float, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
+  return emu_feat_run<float, DynGeom, kWarps>(FEAT_ARGS);
 #undef FEAT_ARGS
 }
 

@@ -1,0 +1,124 @@
+"""The real kernel sources (csrc/*.cuh) on the CPU SIMT emulator vs the oracle.
+
+No GPU is needed: tests/emu compiles stft_kernels.cuh / fft_warp.cuh / host_plan.h with g++ and
+runs thread blocks on OS threads (test infrastructure, never part of the product).  These tests
+pin the kernels' index maths -- warp FFT slot order, conjugate-pair shuffles, tile / edge /
+reflect logic, gather overlap-add -- before any GPU time is spent; the GPU tier repeats the same
+comparisons through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from oracle import librosa_compat as lc
+from oracle import reference_audio as ra
+from single_speaker_tts_b200.synthetic import speech_like_clip
+
+WIN, HOP, NFFT = 1102, 275, 2048
+
+
+@pytest.mark.parametrize('prec,tol', [(0, 5e-7), (1, 1e-14)])
+@pytest.mark.parametrize('inverse', [False, True])
+def test_warp_fft1024(emu, prec, tol, inverse):
+    rng = np.random.default_rng(0)
+    z = rng.normal(size=1024) + 1j * rng.normal(size=1024)
+    got = emu.fft1024(z, inverse=inverse, prec=prec)
+    ref = np.fft.ifft(z) * 1024 if inverse else np.fft.fft(z)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < tol
+
+
+def _gl_case(frames, seed=5):
+    rng = np.random.default_rng(seed)
+    mags, angs = [], []
+    for i, T in enumerate(frames):
+        x = speech_like_clip(HOP * (T - 1) + 5, rng)
+        m = np.abs(lc.stft(x, NFFT, HOP, WIN))
+        assert m.shape[1] == T
+        mags.append(m)
+        angs.append(np.exp(2j * np.pi * np.random.RandomState(i).rand(*m.shape)))
+    return mags, angs
+
+
+@pytest.mark.parametrize('prec,tol', [(1, 5e-7), (0, 5e-6)])
+def test_griffin_lim_tiles_and_edges(emu, prec, tol):
+    """T = 1 (empty output), 2 (multi-bounce reflect), single tiles, merged 9-frame tile, 8+5 split,
+    many tiles; 2 iterations exercise synth, fused step, finalize and the parity buffers."""
+    frames = [1, 2, 5, 9, 13, 30]
+    mags, angs = _gl_case(frames)
+    wavs, mses = emu.griffin_lim(mags, angs, 2, prec=prec, want_mse=True)
+    for T, m, a, w, mse in zip(frames, mags, angs, wavs, mses):
+        assert w.shape == (HOP * (T - 1),)
+        if T == 1:
+            continue
+        ref, rmse = ra.griffin_lim_v2(m, WIN, HOP, NFFT, 2, angles=a, batched_fft=True)
+        assert not np.isnan(w).any()
+        assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < tol
+        assert abs(mse - rmse) / rmse < 1e-5
+
+
+def test_griffin_lim_zero_iterations_is_istft(emu):
+    mags, angs = _gl_case([12])
+    w = emu.griffin_lim(mags, angs, 0, prec=1)[0]
+    ref = lc.istft(mags[0].astype(np.complex128) * angs[0], HOP, WIN)
+    assert np.abs(w - ref).max() < 1e-6 * np.abs(ref).max() + 1e-7
+
+
+def test_griffin_lim_zero_bins_give_unit_phase(emu):
+    """|E| == 0 must yield phase (1, 0) (np.exp(1j*np.angle(0)) == 1, audio/synthesis.py:109)."""
+    T = 6
+    mag = np.zeros((1025, T), np.float32)
+    mag[40, :] = 1.0
+    ang = np.exp(2j * np.pi * np.random.RandomState(3).rand(1025, T))
+    w = emu.griffin_lim([mag], [ang], 2, prec=0)[0]
+    ref = ra.spectrogram_to_wav(mag, WIN, HOP, NFFT, 2, angles=ang)
+    assert not np.isnan(w).any()
+    assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < 1e-4
+
+
+def test_griffin_lim_dynamic_geometry(emu):
+    """A window / hop other than the model's goes through the run-time geometry kernels."""
+    win, hop = 1024, 256
+    x = speech_like_clip(hop * 19 + 3, np.random.default_rng(8))
+    m = np.abs(lc.stft(x, NFFT, hop, win))
+    a = np.exp(2j * np.pi * np.random.RandomState(1).rand(*m.shape))
+    w = emu.griffin_lim([m], [a], 2, prec=1, win=win, hop=hop)[0]
+    ref = ra.spectrogram_to_wav(m, win, hop, NFFT, 2, angles=a)
+    assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < 5e-7
+
+
+@pytest.mark.parametrize('prec,tol_lin', [(1, 5e-7), (0, 2e-3)])
+def test_feature_pipeline(emu, prec, tol_lin):
+    """load_audio core (datasets/lj_speech.py:124-156): ragged clips incl. N = 1, N < hop, N == hop."""
+    rng = np.random.default_rng(7)
+    lens = [1, 2, 274, 275, 1500, 5000]
+    wavs = [speech_like_clip(max(n, 8), rng)[:n] for n in lens]
+    res = emu.stft_features(wavs, prec=prec, r=5, normalize=(35.66, 100.0, 6.02, 99.89))
+    for w, r in zip(wavs, res):
+        S = lc.stft(w, NFFT, HOP, WIN).T
+        assert S.shape[0] == r['T']
+        mel_ref, lin_ref = ra.load_audio_from_wav(w, 22050, trim=False)
+        assert r['lin'].shape == (mel_ref.shape[0] * 5, 1025)
+        assert np.abs(r['lin'] - lin_ref.reshape(-1, 1025)).max() < tol_lin
+        assert np.abs(r['mel'] - mel_ref.reshape(-1, 80)).max() < 2e-6
+        assert np.abs(r['spec'][:r['T']] - S).max() / np.abs(S).max() < (1e-7 if prec else 1e-6)
+        mr = ra.mel_scale_spectrogram(w, NFFT, 22050, 80, 0, 8000, HOP, WIN, 1).T
+        assert np.abs(r['melraw'][:r['T']] - mr).max() / np.abs(mr).max() < 1e-6
+
+
+def test_decibel_statistics_geometry(emu):
+    """datasets/statistics.py:31-51: n_fft 1024 / hop 256 / win 1024, fmax sr//2, embedded in the
+    2048-point transform (every other bin)."""
+    rng = np.random.default_rng(9)
+    wavs = [speech_like_clip(n, rng) for n in (300, 5000, 22050)]
+    res = emu.stft_features(wavs, prec=1, n_fft=1024, win=1024, hop=256, fmax=11025.)
+    for w, r in zip(wavs, res):
+        S = lc.stft(w, 1024, 256, 1024).T
+        assert r['spec'].shape == S.shape
+        assert np.abs(r['spec'] - S).max() / np.abs(S).max() < 1e-7
+        assert np.abs(r['minmax'] - ra.decibel_statistics(w, 22050)).max() < 2e-5
+
+
+def test_mel_basis_matches_oracle(emu):
+    for n_fft, fmax in ((2048, 8000), (1024, 11025)):
+        mb = emu.mel_basis(22050, n_fft, 80, 0, fmax)
+        ref = lc.mel_filterbank(22050, n_fft, 80, 0, fmax)
+        assert np.abs(mb - ref).max() < 1e-15 and ((mb != 0) == (ref != 0)).all()

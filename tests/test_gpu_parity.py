@@ -1,0 +1,225 @@
+"""Parity of the CUDA path (through the public API -> C ABI -> sm_100a kernels) with the oracle.
+
+Tolerances are the ones BASELINE.json:north_star states:
+  * Griffin-Lim waveform: relative L2 <= 1e-3 after 50 iterations in FP32;
+  * normalised spectrograms: max abs error <= 1e-4;
+  * statistics reduction (host float64, listing order): bit-exact given the per-clip rows.
+Run with ``pytest -m gpu`` on the B200 box; nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import librosa_compat as lc
+from oracle import reference_audio as ra
+from single_speaker_tts_b200 import _lib
+from single_speaker_tts_b200.audio import features, synthesis
+from single_speaker_tts_b200.datasets import statistics
+from single_speaker_tts_b200.datasets.dataset_helper import LJSpeechDatasetHelper
+from single_speaker_tts_b200.synthetic import make_clips, speech_like_clip
+
+pytestmark = pytest.mark.gpu
+
+WIN, HOP, NFFT = 1102, 275, 2048
+GL_TOL = 1e-3      # north_star: waveform relative L2 after 50 iterations, FP32
+NORM_TOL = 1e-4    # north_star: normalised spectrogram max abs error
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(1e-30, np.linalg.norm(b)))
+
+
+def _case(frames, seed=5):
+    rng = np.random.default_rng(seed)
+    mags, angs = [], []
+    for i, T in enumerate(frames):
+        x = speech_like_clip(HOP * (T - 1) + 5, rng)
+        m = np.abs(lc.stft(x, NFFT, HOP, WIN))
+        mags.append(m)
+        angs.append(np.exp(2j * np.pi * np.random.RandomState(i).rand(*m.shape)))
+    return mags, angs
+
+
+def test_native_library_is_loaded():
+    lib = _lib.load()
+    assert lib.sstts_device_count() >= 1
+    assert torch.cuda.get_device_capability(0)[0] >= 10, 'kernels are built for sm_100a only'
+
+
+@pytest.mark.parametrize('precision,tol', [('f32', 5e-6), ('f64', 5e-7)])
+def test_griffin_lim_small_ragged(precision, tol):
+    frames = [1, 2, 5, 9, 13, 30, 77]
+    mags, angs = _case(frames)
+    wavs, mses = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 2, angles=angs, precision=precision,
+                                                return_mse=True)
+    for T, m, a, w, mse in zip(frames, mags, angs, wavs, mses):
+        assert w.dtype == np.float32 and w.shape == (HOP * (T - 1),)
+        if T == 1:
+            continue
+        ref, rmse = ra.griffin_lim_v2(m, WIN, HOP, NFFT, 2, angles=a, batched_fft=True)
+        assert rel_l2(w, ref) < tol
+        assert abs(mse - rmse) / rmse < 1e-4
+
+
+def test_griffin_lim_50_iterations_golden_synthetic(golden_dir):
+    g = np.load(golden_dir + '/gl_synthetic.npz')
+    clips = [g['clip%d' % i] for i in range(3)]
+    mags = [np.abs(lc.stft(c, NFFT, HOP, WIN)) for c in clips]
+    angs = [np.exp(2j * np.pi * np.random.RandomState(int(g['seed0']) + i).rand(*m.shape)) for i, m in enumerate(mags)]
+    wavs, mses = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, int(g['n_iter']), angles=angs, return_mse=True)
+    for i, w in enumerate(wavs):
+        assert rel_l2(w, g['wav%d' % i]) <= GL_TOL
+        assert abs(mses[i] - float(g['mse%d' % i])) / float(g['mse%d' % i]) < 1e-2
+
+
+def test_griffin_lim_50_iterations_real_model_output(golden_dir):
+    """The reference's dumped model output through tacotron/inference.py:94-101,175 + 50 iterations."""
+    g = np.load(golden_dir + '/gl_fixture.npz')
+    mag = ra.inference_postprocess(g['model_output'])
+    ang = np.exp(2j * np.pi * np.random.RandomState(int(g['seed'])).rand(*mag.shape))
+    wav, mse = synthesis.griffin_lim_v2(mag, WIN, HOP, NFFT, int(g['n_iter']), angles=ang)
+    assert wav.shape == g['wav'].shape
+    assert rel_l2(wav, g['wav']) <= GL_TOL
+    assert abs(mse - float(g['mse'])) / float(g['mse']) < 1e-2
+
+
+def test_griffin_lim_dropin_uses_numpy_global_rng():
+    x = speech_like_clip(6000, np.random.default_rng(4))
+    mag = np.abs(lc.stft(x, NFFT, HOP, WIN))
+    np.random.seed(123)
+    ref, rmse = ra.griffin_lim_v2(mag, WIN, HOP, NFFT, 5, batched_fft=True)
+    np.random.seed(123)
+    wav, mse = synthesis.griffin_lim_v2(mag, WIN, HOP, NFFT, 5)
+    assert rel_l2(wav, ref) < 1e-5 and abs(mse - rmse) / rmse < 1e-4
+    np.random.seed(123)
+    wav2 = synthesis.spectrogram_to_wav(mag, WIN, HOP, NFFT, 5)
+    assert np.array_equal(wav, wav2)                   # deterministic
+    w0, m0 = synthesis.griffin_lim_v2(mag, WIN, HOP, NFFT, 0)
+    assert m0 is None and w0.shape == ref.shape
+
+
+def test_griffin_lim_batch_invariance_and_layouts():
+    mags, angs = _case([40, 9, 100])
+    batch = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 6, angles=angs)
+    alone = synthesis.spectrograms_to_wavs([mags[2]], WIN, HOP, NFFT, 6, angles=[angs[2]])[0]
+    assert np.array_equal(batch[2], alone)
+    # float64, C-ordered (1025, T) input gives the same result as the float32 F-ordered view
+    m64 = np.ascontiguousarray(mags[0].astype(np.float64))
+    w64 = synthesis.spectrograms_to_wavs([m64], WIN, HOP, NFFT, 6, angles=[angs[0]])[0]
+    assert np.array_equal(w64, batch[0])
+
+
+def test_griffin_lim_dynamic_geometry_and_zero_bins():
+    win, hop = 1024, 256
+    x = speech_like_clip(hop * 40 + 3, np.random.default_rng(8))
+    m = np.abs(lc.stft(x, NFFT, hop, win))
+    a = np.exp(2j * np.pi * np.random.RandomState(1).rand(*m.shape))
+    w = synthesis.spectrogram_to_wav(m, win, hop, NFFT, 3, angles=a)
+    assert rel_l2(w, ra.spectrogram_to_wav(m, win, hop, NFFT, 3, angles=a)) < 5e-6
+    mag = np.zeros((1025, 12), np.float32)
+    mag[40, :] = 1.0
+    ang = np.exp(2j * np.pi * np.random.RandomState(3).rand(1025, 12))
+    w = synthesis.spectrogram_to_wav(mag, WIN, HOP, NFFT, 2, angles=ang)
+    assert np.isfinite(w).all() and rel_l2(w, ra.spectrogram_to_wav(mag, WIN, HOP, NFFT, 2, angles=ang)) < 1e-4
+    wz = synthesis.spectrogram_to_wav(np.zeros((1025, 9), np.float32), WIN, HOP, NFFT, 2)
+    assert np.array_equal(wz, np.zeros(HOP * 8, np.float32))
+
+
+def test_device_random_phase_is_seeded_and_unit():
+    mags, _ = _case([20, 33])
+    a = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3, seed=7)
+    b = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3, seed=7)
+    c = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3, seed=8)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert not np.array_equal(a[0], c[0])
+    np.random.seed(5); d = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3)
+    np.random.seed(5); e = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3)
+    assert all(np.array_equal(x, y) for x, y in zip(d, e))
+
+
+def test_features_golden(golden_dir):
+    f = np.load(golden_dir + '/features.npz')
+    clips = [f['clip%d' % i] for i in range(3)]
+    out = LJSpeechDatasetHelper.features_from_wavs(clips, sampling_rate=22050, trim_silence=False)
+    for i, (mel, lin) in enumerate(out):
+        assert mel.dtype == np.float32 and lin.dtype == np.float32
+        assert mel.shape == f['mel%d' % i].shape and lin.shape == f['lin%d' % i].shape
+        assert np.abs(mel - f['mel%d' % i]).max() <= NORM_TOL
+        assert np.abs(lin - f['lin%d' % i]).max() <= NORM_TOL
+    rows = statistics.decibel_statistics_batch(clips, 22050)
+    for i in range(3):
+        assert np.abs(rows[i] - f['stats%d' % i]).max() < 1e-3
+    assert np.abs(statistics.collect_decibel_statistics_from_wavs(clips, 22050, batch_clips=2) - f['corpus_stats']).max() < 1e-3
+    assert np.array_equal(statistics.reduce_decibel_statistics(rows),
+                          statistics.collect_decibel_statistics_from_wavs(clips, 22050))
+
+
+def test_features_ragged_edge_cases_vs_oracle():
+    rng = np.random.default_rng(7)
+    lens = [1, 2, 274, 275, 276, 1500, 5000, 30000]
+    wavs = [speech_like_clip(max(n, 8), rng)[:n] for n in lens]
+    wavs.append(np.zeros(4000, np.float32))                       # digital silence -> -100 dB floor
+    out = LJSpeechDatasetHelper.features_from_wavs(wavs, sampling_rate=22050, trim_silence=False)
+    for w, (mel, lin) in zip(wavs, out):
+        mel_ref, lin_ref = ra.load_audio_from_wav(w, 22050, trim=False)
+        assert mel.shape == mel_ref.shape and lin.shape == lin_ref.shape
+        assert np.abs(mel - mel_ref).max() <= NORM_TOL and np.abs(lin - lin_ref).max() <= NORM_TOL
+    # with the trim step of datasets/lj_speech.py:119
+    x = np.concatenate([np.zeros(3000, np.float32), wavs[-2], np.zeros(3000, np.float32)])
+    mel, lin = LJSpeechDatasetHelper.features_from_wavs([x], sampling_rate=22050)[0]
+    mel_ref, lin_ref = ra.load_audio_from_wav(x, 22050, trim=True)
+    assert mel.shape == mel_ref.shape and np.abs(lin - lin_ref).max() <= NORM_TOL
+
+
+def test_features_public_functions_vs_oracle():
+    x = speech_like_clip(12345, np.random.default_rng(11))
+    S = features.linear_scale_spectrogram(x, NFFT, HOP, WIN)
+    Sr = ra.linear_scale_spectrogram(x, NFFT, HOP, WIN)
+    assert S.dtype == np.complex64 and S.shape == Sr.shape and S.flags['F_CONTIGUOUS']
+    assert np.abs(S - Sr).max() / np.abs(Sr).max() < 2e-7
+    S2 = features.linear_scale_spectrogram(x, 1024)                 # defaults: win = n_fft, hop = win // 4
+    assert np.abs(S2 - ra.linear_scale_spectrogram(x, 1024)).max() / np.abs(Sr).max() < 2e-7
+    for power in (1, 2):
+        M = features.mel_scale_spectrogram(x, NFFT, 22050, 80, 0, 8000, HOP, WIN, power)
+        Mr = ra.mel_scale_spectrogram(x, NFFT, 22050, 80, 0, 8000, HOP, WIN, power)
+        assert M.dtype == np.float64 and M.shape == Mr.shape
+        assert np.abs(M - Mr).max() / np.abs(Mr).max() < 1e-6
+    st = statistics.decibel_statistics(x, 22050)
+    assert np.abs(st - ra.decibel_statistics(x, 22050)).max() < 1e-3
+    with pytest.raises(ValueError):
+        features.linear_scale_spectrogram(np.zeros((2, 100), np.float32), NFFT, HOP, WIN)
+
+
+def test_features_f32_fast_mode_error_is_bounded():
+    """precision='f32' is the documented fast mode: bins > ~100 dB under the frame peak differ."""
+    x = speech_like_clip(40000, np.random.default_rng(12))
+    mel_ref, lin_ref = ra.load_audio_from_wav(x, 22050, trim=False)
+    mel, lin = LJSpeechDatasetHelper.features_from_wavs([x], 22050, trim_silence=False, precision='f32')[0]
+    assert np.abs(mel - mel_ref).max() < 1e-5
+    assert np.abs(lin - lin_ref).max() < 2e-2 and np.mean(np.abs(lin - lin_ref) > NORM_TOL) < 1e-3
+
+
+def test_full_size_round_trip_properties():
+    """BASELINE configs 1-2 at full size (256 ragged clips): STFT -> (|S|, true phase) -> Griffin-Lim
+    must return the input (a consistent spectrogram is a fixed point of the iteration), every output
+    obeys the hop * (T - 1) length rule, and the feature rows are in [0, 1] with zero pad rows."""
+    clips = make_clips(256, seed=1, pool=8)
+    res = LJSpeechDatasetHelper.features_from_wavs(clips, 22050, trim_silence=False)
+    for c, (mel, lin) in zip(clips[:256:17], res[:256:17]):
+        T = 1 + len(c) // HOP
+        assert lin.shape == (-(-T // 5), 5125) and mel.shape == (-(-T // 5), 400)
+        assert lin.min() >= 0 and lin.max() <= 1 and mel.min() >= 0 and mel.max() <= 1
+        assert np.all(lin.reshape(-1, 1025)[T:] == 0) and np.all(mel.reshape(-1, 80)[T:] == 0)
+    from single_speaker_tts_b200 import _runtime
+    sub = clips[:64]
+    spec = _runtime.stft_features_batch(sub, NFFT, HOP, WIN, want_spec=True, precision='f64')
+    mags, angs = [], []
+    for i in range(len(sub)):
+        S = spec.rows(spec.spec, i).T
+        mags.append(np.abs(S))
+        angs.append(np.where(np.abs(S) > 0, S / np.maximum(np.abs(S), 1e-30), 1.0))
+    for n_iter in (0, 5):
+        wavs = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, n_iter, angles=angs)
+        for c, w in zip(sub, wavs):
+            assert w.shape == (HOP * (len(c) // HOP),)
+            assert rel_l2(w, c[:len(w)]) < 2e-5

@@ -1,0 +1,123 @@
+"""Host-side logic and the C-ABI boundary, without a GPU: the library loads and exports every
+symbol include/sstts.h declares, argument errors surface as Python exceptions, there is no CPU
+fallback, and the numpy-level helpers equal the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import librosa_compat as lc
+from oracle import reference_audio as ra
+from single_speaker_tts_b200 import _lib, _runtime, distributed
+from single_speaker_tts_b200.audio import conversion, effects
+from single_speaker_tts_b200.datasets.dataset_helper import DatasetHelper, LJSpeechDatasetHelper
+from single_speaker_tts_b200.datasets.statistics import reduce_decibel_statistics
+from single_speaker_tts_b200.synthetic import make_clips, speech_like_clip
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'sstts.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(sstts_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.SIGNATURES) == names            # the binding covers exactly the header
+    assert lib.sstts_version() == 100
+
+
+def test_plan_argument_errors_are_reported():
+    lib = _lib.load()
+    cfg = _runtime._make_config(4096, 1102, 275, 'f32')
+    h = ctypes.c_void_p()
+    off = np.array([0, 10], dtype=np.int64)
+    rc = lib.sstts_gl_plan_create(ctypes.byref(cfg), 1, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                  ctypes.byref(h))
+    assert rc == -1 and b'n_fft' in lib.sstts_last_error()
+    with pytest.raises(_lib.SsttsError):
+        _lib.check(rc)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_no_cpu_fallback():
+    from single_speaker_tts_b200.audio import features, synthesis
+    mag = np.ones((1025, 4), np.float32)
+    with pytest.raises(_lib.SsttsError):
+        synthesis.spectrogram_to_wav(mag, 1102, 275, 2048, 1)
+    with pytest.raises(_lib.SsttsError):
+        features.linear_scale_spectrogram(np.zeros(1000, np.float32), 2048, 275, 1102)
+
+
+def test_conversion_module_equals_oracle():
+    rng = np.random.default_rng(0)
+    mag = rng.random((1025, 7)).astype(np.float32) * 3
+    db = conversion.magnitude_to_decibel(mag)
+    assert db.dtype == np.float32 and np.array_equal(db, ra.magnitude_to_decibel(mag))
+    n = conversion.normalize_decibel(db, 35.66, 100.0)
+    assert np.array_equal(n, ra.normalize_decibel(db, 35.66, 100.0))
+    assert np.array_equal(conversion.inv_normalize_decibel(n, 6.02, 99.89), ra.inv_normalize_decibel(n, 6.02, 99.89))
+    assert np.array_equal(conversion.decibel_to_magnitude(db), ra.decibel_to_magnitude(db))
+    with pytest.raises(AssertionError, match='smaller -100 dB'):
+        conversion.decibel_to_magnitude(np.array([-101.0]))
+    assert conversion.ms_to_samples(50.0, 22050) == 1102 and conversion.ms_to_samples(12.5, 22050) == 275
+    assert conversion.samples_to_ms(22050, 22050) == 1000 and conversion.get_duration(np.zeros(44100), 22050) == 2.0
+
+
+def test_trim_equals_oracle():
+    x = np.concatenate([np.zeros(3000, np.float32), speech_like_clip(15000, np.random.default_rng(1)),
+                        1e-5 * np.ones(7000, np.float32)])
+    y, idx = effects.trim(x)
+    yr, idxr = lc.trim(x)
+    assert np.array_equal(idx, idxr) and np.array_equal(y, yr)
+    z, idz = effects.trim(np.zeros(5000, np.float32))
+    assert np.array_equal(idz, lc.trim(np.zeros(5000, np.float32))[1])
+
+
+def test_reduction_padding_equals_oracle():
+    mel = np.random.default_rng(2).random((13, 80)).astype(np.float32)
+    lin = np.random.default_rng(3).random((13, 1025)).astype(np.float32)
+    a = DatasetHelper.apply_reduction_padding(mel, lin, 5)
+    b = ra.apply_reduction_padding(mel, lin, 5)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert (LJSpeechDatasetHelper.mel_mag_ref_db, LJSpeechDatasetHelper.mel_mag_max_db,
+            LJSpeechDatasetHelper.linear_ref_db, LJSpeechDatasetHelper.linear_mag_max_db) == (6.02, 99.89, 35.66, 100.0)
+
+
+def test_shard_by_cost_is_balanced_partition():
+    rng = np.random.default_rng(4)
+    costs = rng.integers(81, 803, 256)
+    for world in (1, 2, 4, 8):
+        shards = distributed.shard_by_cost(costs, world)
+        assert sorted(i for s in shards for i in s) == list(range(256))
+        loads = [costs[s].sum() for s in shards]
+        assert max(loads) - min(loads) <= costs.max()
+
+
+def test_reduce_statistics_is_mean_in_listing_order():
+    rows = np.random.default_rng(5).normal(size=(37, 4)) * 30
+    ref = np.zeros(4)
+    for r in rows:
+        ref += r
+    ref /= len(rows)
+    assert np.array_equal(reduce_decibel_statistics(rows), ref)
+    mean, mn, mx, table = distributed.reduce_corpus_statistics(rows, np.arange(37), 37)
+    assert np.array_equal(mean, ref) and np.array_equal(mn, rows.min(0)) and np.array_equal(mx, rows.max(0))
+
+
+def test_synthetic_clips_are_seeded_and_shaped():
+    a = make_clips(4, seed=1)
+    b = make_clips(4, seed=1)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert all(x.dtype == np.float32 and 22050 <= len(x) <= 220500 and abs(np.abs(x).max() - 0.5) < 1e-6 for x in a)
+    c = make_clips(6, seed=2, kind='ljspeech', pool=2)
+    assert all(int(1.11 * 22050) <= len(x) <= int(10.1 * 22050) + 1 for x in c)
