@@ -5,7 +5,7 @@
 // 32 x 32 Cooley-Tukey split:
 //     pass 1  32-point FFT over the register index, entirely in registers
 //     twiddle W_1024^(l * k1)   (table in shared memory, conflict-free [k1][l] layout)
-//     32 x 32 transpose through a padded per-warp shared-memory tile (the only exchange)
+//     32 x 32 transpose through a padded per-warp shared-memory plane (the only exchange)
 //     pass 2  32-point FFT over the register index again
 // Input and output use the same "element = 32 * slot + lane" indexing.  Two flavours:
 //     DIF (analysis):   natural slot order in, bit-reversed slot order out
@@ -128,39 +128,40 @@ SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
   }
 }
 
-// Row pitch (in complex elements) of the per-warp transpose tile: 33 keeps both the
-// column-wise stores and the row-wise loads bank-conflict free for 8- and 16-byte elements.
+// Per-warp transpose tile: one scalar plane of 32 x 33 (pitch 33 keeps the column-wise stores
+// and the row-wise loads bank-conflict free).  Real and imaginary parts go through the same
+// plane one after the other, which halves the shared memory per warp compared with a complex
+// tile at the same number of shared-memory wavefronts.
 constexpr int XPITCH = 33;
-constexpr int XTILE_ELEMS = 32 * XPITCH;
+constexpr int XPLANE_ELEMS = 32 * XPITCH;
 
 // 1024-point complex FFT across one warp; element index = 32 * slot + lane on both sides.
 //   DIT = false: slots natural in, bit-reversed out.   DIT = true: bit-reversed in, natural out.
-// tw[a * 32 + b] = exp(-2 pi i a b / 1024); xt is this warp's private XTILE_ELEMS tile.
+// tw[a * 32 + b] = exp(-2 pi i a b / 1024); xp is this warp's private XPLANE_ELEMS plane.
 template <typename T, bool INV, bool DIT>
-SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], typename cx_of<T>::type* xt,
-                          const typename cx_of<T>::type* tw, int lane) {
+SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], T* xp, const typename cx_of<T>::type* tw,
+                          int lane) {
   typedef typename cx_of<T>::type C;
   fft32<T, INV, DIT>(re, im);
 #pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) {
+  for (int k1 = 1; k1 < 32; ++k1) {
     const int p = DIT ? k1 : brev5(k1);  // slot holding pass-1 result k1
-    C v;
-    if (k1 == 0) {
-      v.x = re[p]; v.y = im[p];
-    } else {
-      const C w = tw[k1 * 32 + lane];
-      if (!INV) { v.x = re[p] * w.x - im[p] * w.y; v.y = re[p] * w.y + im[p] * w.x; }
-      else      { v.x = re[p] * w.x + im[p] * w.y; v.y = im[p] * w.x - re[p] * w.y; }
-    }
-    xt[k1 * XPITCH + lane] = v;
+    const C w = tw[k1 * 32 + lane];
+    const T vr = re[p], vi = im[p];
+    if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
+    else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
   }
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = re[DIT ? k1 : brev5(k1)];
   __syncwarp();
 #pragma unroll
-  for (int n2 = 0; n2 < 32; ++n2) {
-    const C v = xt[lane * XPITCH + n2];
-    const int q = DIT ? brev5(n2) : n2;  // slot expected by pass 2 for element n2
-    re[q] = v.x; im[q] = v.y;
-  }
+  for (int n2 = 0; n2 < 32; ++n2) re[DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = im[DIT ? k1 : brev5(k1)];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) im[DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
   __syncwarp();
   fft32<T, INV, DIT>(re, im);
 }

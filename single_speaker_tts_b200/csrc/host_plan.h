@@ -11,31 +11,28 @@
 
 namespace sstts {
 
-// Frames per tile.  Eight frames = one round of an 8-warp CTA; the tail tile of an utterance
-// may hold up to 2 * kMinTile - 1 extra frames, see split_frames().
+// Frames per tile = warps per CTA: every tile is processed in one round, one frame per warp.
 constexpr int kTileFrames = 8;
 constexpr int kWarps = 8;
 
+// Smallest tile of a multi-tile utterance: (ft + 1) * hop >= win keeps same-parity spans and a
+// tile's two edge regions disjoint (>= 4 for win 1102 / hop 275).
 inline int min_tile_frames(int win, int hop) {
-  int v = (win + hop - 1) / hop;  // frames overlapping one sample
-  return v < 4 ? 4 : v;
+  int v = (win + hop - 1) / hop - 1;
+  return v < 2 ? 2 : v;
 }
 
-// Split n_frames into consecutive tiles of `tile` frames; a remainder shorter than `min_tile`
-// borrows frames from its predecessor so every tile of a multi-tile utterance has >= min_tile.
+// Split n_frames into consecutive tiles of at most `tile` frames (one frame per warp); a
+// remainder shorter than `min_tile` borrows frames from its predecessor so every tile of a
+// multi-tile utterance has >= min_tile frames (needs tile >= 2 * min_tile).
 inline void split_frames(int n_frames, int tile, int min_tile, std::vector<std::pair<int, int> >& out) {
   out.clear();
   if (n_frames <= 0) return;
-  if (n_frames <= tile) { out.push_back(std::make_pair(0, n_frames)); return; }
   int a = 0;
   while (a < n_frames) {
     int b = a + tile;
-    if (b >= n_frames) { b = n_frames; }
-    else if (n_frames - b < min_tile) {
-      // leave exactly min_tile frames for the last tile
-      b = n_frames - min_tile;
-      if (b - a < min_tile) b = n_frames;  // cannot split sensibly: merge into one tile
-    }
+    if (b >= n_frames) b = n_frames;
+    else if (n_frames - b < min_tile) b = n_frames - min_tile;   // (tile - (min_tile - r), min_tile)
     out.push_back(std::make_pair(a, b));
     a = b;
   }
@@ -53,7 +50,7 @@ inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int h
   if (win < 2 || win > NFFT || hop < 1 || hop > win) { err = "need 1 <= hop <= win <= n_fft"; return false; }
   if ((NFFT - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
   const int min_tile = min_tile_frames(win, hop);
-  if (min_tile > kTileFrames) { err = "win_length / hop_length > 8 is not supported"; return false; }
+  if (2 * min_tile > kTileFrames) { err = "win_length / hop_length > 5 is not supported"; return false; }
   P.n_utts = n_utts; P.win = win; P.hop = hop;
   P.frame_off.assign(frame_off, frame_off + n_utts + 1);
   P.pad_off.assign(n_utts + 1, 0);

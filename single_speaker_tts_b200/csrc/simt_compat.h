@@ -14,4 +14,12 @@
 #define SSTTS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define SSTTS_HD __host__ __device__ __forceinline__
 #define SSTTS_D __device__ __forceinline__
+// 16-byte asynchronous global -> shared copy (LDGSTS); both addresses 16-byte aligned.
+__device__ __forceinline__ void sstts_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void sstts_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
 #endif

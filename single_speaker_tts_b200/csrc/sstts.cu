@@ -239,10 +239,11 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   A.mse_frame = nullptr;
   A.win = H.win; A.hop = H.hop; A.span_max = H.span_max;
 
-  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.span_max);
-  int occ_s = 0, occ_i = 0, rc;
-  if ((rc = configure_kernel(gl_step_kernel<T, G, W, true>, W * 32, smem, &occ_s))) return rc;
-  if ((rc = configure_kernel(gl_step_kernel<T, G, W, false>, W * 32, smem, &occ_i))) return rc;
+  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.hop, H.span_max);
+  int occ_s = 0, occ_i = 0, occ_m = 0, rc;
+  if ((rc = configure_kernel(gl_step_kernel<T, G, W, true, false>, W * 32, smem, &occ_s))) return rc;
+  if ((rc = configure_kernel(gl_step_kernel<T, G, W, false, false>, W * 32, smem, &occ_i))) return rc;
+  if (mse_frame && (rc = configure_kernel(gl_step_kernel<T, G, W, false, true>, W * 32, smem, &occ_m))) return rc;
   const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
   int grid_s = n_sms * occ_s, grid_i = n_sms * occ_i;
   if (grid_s > A.n_tiles) grid_s = A.n_tiles;
@@ -250,14 +251,20 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
 
   // step 0: random phase -> wave_1 (written to buf[0], buf[1])
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
-  gl_step_kernel<T, G, W, true><<<grid_s, W * 32, smem, st>>>(A);
+  gl_step_kernel<T, G, W, true, false><<<grid_s, W * 32, smem, st>>>(A);
   CU(cudaGetLastError());
   int cur = 0;
   for (int it = 0; it < n_iter; ++it) {
     A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
     A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
-    A.mse_frame = (it == n_iter - 1) ? mse_frame : nullptr;
-    gl_step_kernel<T, G, W, false><<<grid_i, W * 32, smem, st>>>(A);
+    if (it == n_iter - 1 && mse_frame) {
+      A.mse_frame = mse_frame;
+      int grid_m = n_sms * occ_m;
+      if (grid_m > A.n_tiles) grid_m = A.n_tiles;
+      gl_step_kernel<T, G, W, false, true><<<grid_m, W * 32, smem, st>>>(A);
+    } else {
+      gl_step_kernel<T, G, W, false, false><<<grid_i, W * 32, smem, st>>>(A);
+    }
     CU(cudaGetLastError());
     cur ^= 1;
   }
@@ -270,7 +277,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   F.win = H.win; F.hop = H.hop;
   int grid_f = n_sms * 8;
   if (grid_f > A.n_tiles) grid_f = A.n_tiles;
-  gl_finalize_kernel<T, G, 256><<<grid_f, 256, sizeof(T) * H.win, st>>>(F);
+  gl_finalize_kernel<T, G, 256><<<grid_f, 256, sizeof(T) * (round_up4(H.win) + round_up4(H.hop)), st>>>(F);
   CU(cudaGetLastError());
   return 0;
 }
@@ -366,9 +373,9 @@ int sstts_griffin_lim(const sstts_gl_plan* P, const float* mag_dev, const float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   if (P->cfg.precision == SSTTS_F64) {
-    return model ? run_griffin_lim<double, ModelGeom, 4>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
+    return model ? run_griffin_lim<double, ModelGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
                                                          wav_out_dev, mse_frame_dev, st)
-                 : run_griffin_lim<double, DynGeom, 4>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
+                 : run_griffin_lim<double, DynGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
                                                        wav_out_dev, mse_frame_dev, st);
   }
   return model ? run_griffin_lim<float, ModelGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
@@ -459,9 +466,9 @@ int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const ss
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   const bool stats = is_stats_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   if (P->cfg.precision == SSTTS_F64) {
-    if (model) return run_features<double, ModelGeom, 4>(P, wav_dev, out, st);
-    if (stats) return run_features<double, StatsGeom, 4>(P, wav_dev, out, st);
-    return run_features<double, DynGeom, 4>(P, wav_dev, out, st);
+    if (model) return run_features<double, ModelGeom, kWarps>(P, wav_dev, out, st);
+    if (stats) return run_features<double, StatsGeom, kWarps>(P, wav_dev, out, st);
+    return run_features<double, DynGeom, kWarps>(P, wav_dev, out, st);
   }
   if (model) return run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st);
   if (stats) return run_features<float, StatsGeom, kWarps>(P, wav_dev, out, st);

@@ -100,10 +100,35 @@ SSTTS_D T window_sumsq(int p, int n_frames, int hop, int win, int lpad, const T*
 // np.finfo(np.float32).tiny -- librosa's guard for the window-sum division.
 #define SSTTS_F32_TINY 1.17549435e-38f
 
+// Reciprocal window sums for samples all of whose covering frames exist ("interior"): they only
+// depend on (p - lpad) mod hop.  Same ascending-frame summation order as window_sumsq().
+template <typename T>
+SSTTS_D void fill_interior_rwss(T* s_rw, const T* s_win, int hop, int win, int tid, int nthreads) {
+  for (int r = tid; r < hop; r += nthreads) {
+    T acc = T(0);
+    for (int j = (win - 1 - r) / hop; j >= 0; --j) {
+      const T w = s_win[r + j * hop];
+      acc += w * w;
+    }
+    s_rw[r] = acc > T(SSTTS_F32_TINY) ? T(1) / acc : T(1);
+  }
+}
+
+// Overlap-add sum -> waveform sample at padded coordinate p (divide by the window sum where it
+// exceeds tiny, as librosa.istft does).
+template <typename T>
+SSTTS_D T normalise_ola(T v, int p, int n_frames, int hop, int win, int lpad, const T* s_win,
+                        const T* s_rw) {
+  const int x = p - lpad;
+  if (x >= win - hop && x / hop <= n_frames - 1) return v * s_rw[x % hop];
+  const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
+  return wss > T(SSTTS_F32_TINY) ? v / wss : v;
+}
+
 // =============================================================================================
 // Griffin-Lim
 // =============================================================================================
-struct GLTile { int utt, a, b, parity; };  // frames [a, b) of utterance utt
+struct GLTile { int utt, a, b, parity; };  // frames [a, b) of utterance utt, b - a <= 8
 
 template <typename T> struct GLArgs {
   const float* mag;              // (sum T, 1025) frame-major |S|
@@ -115,7 +140,7 @@ template <typename T> struct GLArgs {
   const GLTile* tiles;
   int n_tiles;
   StftTables<T> tab;
-  double* mse_frame;             // [sum T] per-frame sum_k (|S| - |E|)^2 or nullptr
+  double* mse_frame;             // [sum T] per-frame sum_k (|S| - |E|)^2 (WANT_MSE launch only)
   int win, hop, span_max;
 };
 
@@ -124,16 +149,32 @@ template <> SSTTS_D float fast_rsqrt<float>(float x) { return rsqrtf(x); }
 template <> SSTTS_D double fast_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
 
 // Unit phasor of (xr, xi) times s;  (1, 0) * s when the bin is exactly zero
-// (np.exp(1j * np.angle(0)) == 1, audio/synthesis.py:109).
+// (np.exp(1j * np.angle(0)) == 1, audio/synthesis.py:109).  Branch-free.
 template <typename T>
 SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
-  m2 = xr * xr + xi * xi;
-  if (m2 > T(0)) {
-    const T inv = fast_rsqrt<T>(m2) * s;
-    yr = xr * inv; yi = xi * inv;
-  } else {
-    yr = s; yi = T(0);
-  }
+  m2 = fma(xr, xr, xi * xi);   // explicit contraction: identical bits in every instantiation
+  const bool nz = m2 > T(0);
+  const T inv = nz ? fast_rsqrt<T>(m2) * s : T(0);
+  yr = nz ? xr * inv : s;
+  yi = xi * inv;
+}
+
+constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
+
+// Asynchronously stage one 1025-float row into shared memory (16-byte LDGSTS for the aligned
+// body, plain loads for the <= 3 + 3 ragged elements).  Element e lands at dst[e + mis]; returns
+// mis.  Completion: sstts_cp_async_wait_all() + __syncwarp().
+SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane) {
+  const int mis = (int)((reinterpret_cast<uintptr_t>(g) >> 2) & 3);
+  const int c_lo = (mis + 3) >> 2;
+  const int c_hi = ((NBINS - 4 + mis) >> 2) + 1;      // chunks c_lo <= c < c_hi lie inside the row
+  const float* gal = g - mis;
+  for (int c = c_lo + lane; c < c_hi; c += 32) sstts_cp_async16(dst + 4 * c, gal + 4 * c);
+  const int head = 4 * c_lo - mis;                     // elements [0, head)
+  if (lane < head) dst[lane + mis] = g[lane];
+  const int tail0 = 4 * c_hi - mis;                    // elements [tail0, NBINS)
+  if (tail0 + lane < NBINS) dst[tail0 + lane + mis] = g[tail0 + lane];
+  return mis;
 }
 
 // The per-frame core of one Griffin-Lim step, on the packed spectrum held by the warp.
@@ -147,11 +188,11 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
 // Lane l owns k = l + 32 k2; for k2 < 16 its partner bin N - k sits in lane (32 - l) & 31,
 // slot 31 - k2 (lane 0: its own slot 32 - k2; k = 0 pairs with the Nyquist bin; k = 512 is
 // self-conjugate).  Each lane processes its 16 low pairs and swaps results with its partner.
-template <typename T, bool FROM_PHASE>
-SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ mrow,
+// srow[k] is |S| of this frame (shared memory for the iteration kernel, global for the synth).
+template <typename T, bool FROM_PHASE, bool WANT_MSE>
+SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
                            const float2* __restrict__ prow,
-                           const typename cx_of<T>::type* s_w2k, int lane, bool want_mse,
-                           double& mse_acc) {
+                           const typename cx_of<T>::type* s_w2k, int lane, double& mse_acc) {
   typedef typename cx_of<T>::type C;
   const int partner = (32 - lane) & 31;
 #pragma unroll
@@ -162,8 +203,8 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ m
     const int k = lane + 32 * k2;
     const int kn = HALF - k;
     const C w = s_w2k[k];
-    const T sk = fabs((T)mrow[k]);
-    const T sn = fabs((T)mrow[kn]);
+    const T sk = fabs((T)srow[k]);
+    const T sn = fabs((T)srow[kn]);
     T ykr, yki, ynr, yni;
     if (!FROM_PHASE) {
       const T zr = re[sl_mine], zi = im[sl_mine];
@@ -179,7 +220,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ m
       T m2k, m2n;
       replace_magnitude<T>(xkr, xki, sk, ykr, yki, m2k);
       replace_magnitude<T>(xnr, xni, sn, ynr, yni, m2n);
-      if (want_mse) {
+      if (WANT_MSE) {
         const double ek = (double)sk - 0.5 * sqrt((double)m2k);
         const double en = (double)sn - 0.5 * sqrt((double)m2n);
         mse_acc += ek * ek + en * en;
@@ -208,12 +249,12 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ m
   // k = 512 (lane 0, slot 16): X = conj(Z), Z' = conj(Y).
   if (lane == 0) {
     const int sl = brev5(16);
-    const T s = fabs((T)mrow[HALF / 2]);
+    const T s = fabs((T)srow[HALF / 2]);
     T yr, yi;
     if (!FROM_PHASE) {
       T m2;
       replace_magnitude<T>(T(2) * re[sl], T(-2) * im[sl], s, yr, yi, m2);
-      if (want_mse) {
+      if (WANT_MSE) {
         const double e = (double)s - 0.5 * sqrt((double)m2);
         mse_acc += e * e;
       }
@@ -225,125 +266,187 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* __restrict__ m
   }
 }
 
+// Shared-memory carve-up of the Griffin-Lim step kernel.
+template <typename T> struct GLSmem {
+  typedef typename cx_of<T>::type C;
+  int plane_elems;   // per-warp plane: transpose tile, later the windowed output frame
+  size_t off_w2k, off_win, off_rw, off_plane, off_mag, off_yin, total;
+  SSTTS_HD GLSmem(int warps, int win, int hop, int span_max) {
+    plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
+    size_t o = sizeof(C) * 1024;
+    off_w2k = o; o += sizeof(C) * 512;
+    off_win = o; o += sizeof(T) * round_up4(win);
+    off_rw = o; o += sizeof(T) * round_up4(hop);
+    off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
+    off_mag = o; o += sizeof(float) * (size_t)warps * MAGROW;
+    off_yin = o; o += sizeof(T) * round_up4(span_max);
+    total = o;
+  }
+};
+
 // One Griffin-Lim step over all tiles.  FROM_PHASE = true is the initial synthesis from the
-// random phase (no analysis half).  W warps per CTA, one frame per warp per round.
-template <typename T, typename G, int W, bool FROM_PHASE>
+// random phase (no analysis half).  W warps per CTA, one frame per warp, tiles of <= W frames.
+template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE>
 __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, NFFT);
   const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const int mlo = lpad & ~1;          // even base of the output-frame slot (8-byte stores)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = W * 32;
 
   SSTTS_DYN_SMEM(smem);
+  const GLSmem<T> L(W, win, hop, A.span_max);
   C* s_tw = reinterpret_cast<C*>(smem);
-  C* s_w2k = s_tw + 1024;
-  C* s_xt = s_w2k + 1024;
-  T* s_win = reinterpret_cast<T*>(s_xt + W * XTILE_ELEMS);
-  T* s_yin = s_win + round_up4(win);
-  T* s_yout = s_yin + round_up4(A.span_max);
+  C* s_w2k = reinterpret_cast<C*>(smem + L.off_w2k);
+  T* s_win = reinterpret_cast<T*>(smem + L.off_win);
+  T* s_rw = reinterpret_cast<T*>(smem + L.off_rw);
+  T* s_planes = reinterpret_cast<T*>(smem + L.off_plane);
+  float* s_mag = reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
+  T* s_yin = reinterpret_cast<T*>(smem + L.off_yin);
+  T* plane = s_planes + warp * L.plane_elems;
 
-  for (int i = tid; i < 1024; i += NT) { s_tw[i] = A.tab.tw1024[i]; s_w2k[i] = A.tab.w2048[i]; }
+  for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
+  for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
   for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
   __syncthreads();
+  fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
+  __syncthreads();
 
-  C* xt = s_xt + warp * XTILE_ELEMS;
   const T syn_scale = T(1.0 / NFFT);
 
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+  // Stage the analysis input of a tile: x_pad[span] = y_norm[reflect], y_norm = OLA sum / wss.
+  auto stage = [&](int tile) {
     const GLTile tl = A.tiles[tile];
     const long long f0 = A.frame_off[tl.utt];
     const int n_frames = (int)(A.frame_off[tl.utt + 1] - f0);
     const long long poff = A.pad_off[tl.utt];
-    const int a = tl.a, b = tl.b, FT = b - a;
-    const int L = hop * (n_frames - 1);
+    const int a = tl.a, b = tl.b;
+    const int L_out = hop * (n_frames - 1);
     const int span_lo = a * hop + lpad;
-    const int span = (FT - 1) * hop + win;
+    const int span = (b - a - 1) * hop + win;
     const T* pin_own = (tl.parity ? A.pin1 : A.pin0) + poff;
     const T* pin_oth = (tl.parity ? A.pin0 : A.pin1) + poff;
-    T* pout_own = (tl.parity ? A.pout1 : A.pout0) + poff;
-
-    if (!FROM_PHASE) {
-      // Stage the analysis input x_pad[span] = y_norm[reflect], y_norm = OLA sum / window sum.
-      const int left_end = (a - 1) * hop + lpad + win;   // previous tile reaches below this
-      const int right_beg = b * hop + lpad;              // next tile reaches from here
+    // tile-relative edge regions: below `le` the previous tile's frames reach in, from `rb` on the
+    // next tile's (disjoint because tiles hold >= min_tile frames)
+    const int le = a > 0 ? win - hop : 0;
+    const int rb = b < n_frames ? (b - a) * hop : 0x7fffffff;
+    // common case: no reflection inside the span and every sample covered by a full set of frames
+    const bool plain = (span_lo >= HALF) && (span_lo + span - HALF <= L_out) && (a * hop >= win - hop) &&
+                       ((a * hop + span - 1) / hop <= n_frames - 1);
+    if (plain) {
+      const T* own = pin_own + span_lo;
+      const T* oth = pin_oth + span_lo;
+      int r = tid % hop;                 // (span_lo - lpad + s) mod hop with span_lo - lpad = a * hop
+#pragma unroll 4
+      for (int s = tid; s < span; s += NT) {
+        T v = own[s];
+        if (s < le || s >= rb) v += oth[s];
+        s_yin[s] = v * s_rw[r];
+        r += NT;
+        if (r >= hop) r %= hop;
+      }
+    } else {
       for (int s = tid; s < span; s += NT) {
         int q = span_lo + s - HALF;
-        if (q < 0 || q >= L) q = reflect_index(q, L);
+        if (q < 0 || q >= L_out) q = reflect_index(q, L_out);
         const int p = q + HALF;
+        const int sp = p - span_lo;      // reflected position relative to this tile's span
         T v = pin_own[p];
-        if (a > 0 && p < left_end) v += pin_oth[p];
-        if (b < n_frames && p >= right_beg) v += pin_oth[p];
-        const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
-        if (wss > T(SSTTS_F32_TINY)) v = v / wss;
-        s_yin[s] = v;
+        if (sp < le || sp >= rb) v += pin_oth[p];
+        s_yin[s] = normalise_ola<T>(v, p, n_frames, hop, win, lpad, s_win, s_rw);
       }
     }
-    for (int s = tid; s < span; s += NT) s_yout[s] = T(0);
-    __syncthreads();
+  };
 
-    const int n_rounds = (FT + W - 1) / W;
-    for (int r = 0; r < n_rounds; ++r) {
-      const int jr = r * W + warp;
-      if (jr < FT) {
-        const long long row = f0 + a + jr;
-        const float* mrow = A.mag + row * NBINS;
-        const float2* prow = FROM_PHASE ? A.phase0 + row * NBINS : nullptr;
-        T re[32], im[32];
-        if (!FROM_PHASE) {
-          const T* fin = s_yin + jr * hop - lpad;  // fin[m], m in [lpad, lpad + win)
-#pragma unroll
-          for (int n1 = 0; n1 < 32; ++n1) {
-            const int m = 64 * n1 + 2 * lane;
-            const int i = m - lpad;
-            re[n1] = (i >= 0 && i < win) ? fin[m] * s_win[i] : T(0);
-            im[n1] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * s_win[i + 1] : T(0);
-          }
-          warp_fft1024<T, false, false>(re, im, xt, s_tw, lane);
-        }
-        double mse_acc = 0.0;
-        const bool want_mse = (!FROM_PHASE) && (A.mse_frame != nullptr);
-        gl_frame_core<T, FROM_PHASE>(re, im, mrow, prow, s_w2k, lane, want_mse, mse_acc);
-        if (want_mse) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
-          if (lane == 0) A.mse_frame[row] = mse_acc;
-        }
-        warp_fft1024<T, true, true>(re, im, xt, s_tw, lane);
-        T* slot = reinterpret_cast<T*>(xt);  // the transpose tile is dead now: reuse as frame slot
+  int tile = blockIdx.x;
+  if (!FROM_PHASE && tile < A.n_tiles) stage(tile);
+  __syncthreads();
+
+  while (tile < A.n_tiles) {
+    const GLTile tl = A.tiles[tile];
+    const long long f0 = A.frame_off[tl.utt];
+    const long long poff = A.pad_off[tl.utt];
+    const int a = tl.a, FT = tl.b - tl.a;
+    const int span_lo = a * hop + lpad;
+    const int span = (FT - 1) * hop + win;
+    T* pout_own = (tl.parity ? A.pout1 : A.pout0) + poff;
+
+    if (warp < FT) {
+      const long long row = f0 + a + warp;
+      const float* mrow = A.mag + row * NBINS;
+      const float2* prow = FROM_PHASE ? A.phase0 + row * NBINS : nullptr;
+      const float* srow = mrow;
+      T re[32], im[32];
+      if (!FROM_PHASE) {
+        const int mis = stage_row_async(s_mag, mrow, lane);
+        srow = s_mag + mis;
+        const T* fin = s_yin + warp * hop - lpad;  // fin[m], m in [lpad, lpad + win)
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
-          const int i = 64 * n1 + 2 * lane - lpad;
-          if (i >= 0 && i < win) slot[i] = re[n1] * (s_win[i] * syn_scale);
-          if (i + 1 >= 0 && i + 1 < win) slot[i + 1] = im[n1] * (s_win[i + 1] * syn_scale);
+          const int m = 64 * n1 + 2 * lane;
+          const int i = m - lpad;
+          re[n1] = (i >= 0 && i < win) ? fin[m] * s_win[i] : T(0);
+          im[n1] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * s_win[i + 1] : T(0);
+        }
+        warp_fft1024<T, false, false>(re, im, plane, s_tw, lane);
+        sstts_cp_async_wait_all();
+        __syncwarp();
+      }
+      double mse_acc = 0.0;
+      gl_frame_core<T, FROM_PHASE, WANT_MSE>(re, im, srow, prow, s_w2k, lane, mse_acc);
+      if (WANT_MSE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
+        if (lane == 0) A.mse_frame[row] = mse_acc;
+      }
+      warp_fft1024<T, true, true>(re, im, plane, s_tw, lane);
+      // windowed output frame into the (now dead) plane; slot index = m - mlo, zero outside
+      // the window so that the pair store needs no per-element guard
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const int m = 64 * n1 + 2 * lane;
+        const int i = m - lpad;
+        if (m >= mlo && m < lpad + win + 1) {
+          const T v0 = (i >= 0 && i < win) ? re[n1] * (s_win[i] * syn_scale) : T(0);
+          const T v1 = (i + 1 >= 0 && i + 1 < win) ? im[n1] * (s_win[i + 1] * syn_scale) : T(0);
+          plane[m - mlo] = v0;
+          plane[m - mlo + 1] = v1;
         }
       }
-      __syncthreads();
-      // Gather-accumulate this round's frames into the tile's overlap-add buffer.
-      const int jr0 = r * W;
-      const int jr1 = (jr0 + W < FT) ? jr0 + W : FT;
-      const int s_hi = (jr1 - 1) * hop + win;
-      for (int s = jr0 * hop + tid; s < s_hi; s += NT) {
-        int f_hi = s / hop;
-        if (f_hi > jr1 - 1) f_hi = jr1 - 1;
-        const int num = s - win + 1;
-        int f_lo = num <= 0 ? 0 : (num + hop - 1) / hop;
-        if (f_lo < jr0) f_lo = jr0;
-        T acc = s_yout[s];
-        for (int f = f_lo; f <= f_hi; ++f)
-          acc += reinterpret_cast<const T*>(s_xt + (f - jr0) * XTILE_ELEMS)[s - f * hop];
-        s_yout[s] = acc;
-      }
-      __syncthreads();
     }
-    for (int s = tid; s < span; s += NT) pout_own[span_lo + s] = s_yout[s];
     __syncthreads();
+    // Gather overlap-add (ascending frame order, no atomics) straight to the parity buffer:
+    // sample s = q * hop + r receives frame q - j at offset r + j * hop, j = jmax .. 0.
+    {
+      const int dl = lpad - mlo;
+      const int pe = L.plane_elems;
+      const int jmax = (win - 1) / hop;
+      T* dst = pout_own + span_lo;
+      int q = tid / hop, r = tid % hop;
+#pragma unroll 2
+      for (int s = tid; s < span; s += NT) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = jmax; j >= 0; --j) {
+          const int f = q - j;
+          const int off = r + j * hop;
+          if (f >= 0 && f < FT && off < win) acc += s_planes[f * pe + off + dl];
+        }
+        dst[s] = acc;
+        r += NT;
+        if (r >= hop) { q += r / hop; r %= hop; }
+      }
+    }
+    const int next = tile + gridDim.x;
+    if (!FROM_PHASE && next < A.n_tiles) stage(next);
+    __syncthreads();
+    tile = next;
   }
 }
 
-template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int span_max) {
-  return sizeof(typename cx_of<T>::type) * (size_t)(2048 + warps * XTILE_ELEMS) +
-         sizeof(T) * (size_t)(round_up4(win) + 2 * round_up4(span_max));
+template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int hop, int span_max) {
+  return GLSmem<T>(warps, win, hop, span_max).total;
 }
 
 // Partial sums -> normalised, centre-trimmed float32 waveform (the reference's final istft
@@ -364,29 +467,30 @@ __global__ void __launch_bounds__(NT) gl_finalize_kernel(const GLFinalArgs<T> A)
   const int tid = threadIdx.x;
   SSTTS_DYN_SMEM(smem);
   T* s_win = reinterpret_cast<T*>(smem);
+  T* s_rw = s_win + round_up4(win);
   for (int i = tid; i < win; i += NT) s_win[i] = A.window[i];
+  __syncthreads();
+  fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
   __syncthreads();
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
     const GLTile tl = A.tiles[tile];
     const long long f0 = A.frame_off[tl.utt];
     const int n_frames = (int)(A.frame_off[tl.utt + 1] - f0);
     const long long poff = A.pad_off[tl.utt];
-    const int L = hop * (n_frames - 1);
+    const int L_out = hop * (n_frames - 1);
     const int a = tl.a, b = tl.b;
     const T* pin_own = (tl.parity ? A.pin1 : A.pin0) + poff;
     const T* pin_oth = (tl.parity ? A.pin0 : A.pin1) + poff;
     float* out = A.wav_out + A.sample_off[tl.utt];
     int p_lo = a * hop + lpad;
     if (p_lo < HALF) p_lo = HALF;
-    int p_hi = (b < n_frames) ? b * hop + lpad : HALF + L;
-    if (p_hi > HALF + L) p_hi = HALF + L;
+    int p_hi = (b < n_frames) ? b * hop + lpad : HALF + L_out;
+    if (p_hi > HALF + L_out) p_hi = HALF + L_out;
     const int left_end = (a - 1) * hop + lpad + win;
     for (int p = p_lo + tid; p < p_hi; p += NT) {
       T v = pin_own[p];
       if (a > 0 && p < left_end) v += pin_oth[p];
-      const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
-      if (wss > T(SSTTS_F32_TINY)) v = v / wss;
-      out[p - HALF] = (float)v;
+      out[p - HALF] = (float)normalise_ola<T>(v, p, n_frames, hop, win, lpad, s_win, s_rw);
     }
   }
 }
@@ -447,6 +551,8 @@ template <> struct feat_math<double> {
   static SSTTS_D double mel_db(double m) { return 20.0 * log10(fmax(1e-5, m)); }
 };
 
+constexpr int FEAT_PLANE_ELEMS = 1056;  // >= XPLANE_ELEMS and >= NBINS floats
+
 template <typename T, typename G, int W>
 __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> A) {
   typedef typename cx_of<T>::type C;
@@ -460,15 +566,16 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   SSTTS_DYN_SMEM(smem);
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = s_tw + 1024;
-  C* s_xt = s_w2k + 1024;
-  T* s_win = reinterpret_cast<T*>(s_xt + W * XTILE_ELEMS);
+  T* s_planes = reinterpret_cast<T*>(s_w2k + 512);
+  T* s_win = s_planes + W * FEAT_PLANE_ELEMS;
   float* s_x = reinterpret_cast<float*>(s_win + round_up4(win));
 
-  for (int i = tid; i < 1024; i += NT) { s_tw[i] = A.tab.tw1024[i]; s_w2k[i] = A.tab.w2048[i]; }
+  for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
+  for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
   for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
   __syncthreads();
 
-  C* xt = s_xt + warp * XTILE_ELEMS;
+  T* plane = s_planes + warp * FEAT_PLANE_ELEMS;
   const bool want_lin = A.lin_out != nullptr;
   const bool want_mel = (A.mel_out != nullptr) || (A.melraw_out != nullptr) ||
                         (A.minmax_out != nullptr);
@@ -512,9 +619,8 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
         re[n1] = (i >= 0 && i < win) ? (T)fin[m] * s_win[i] : T(0);
         im[n1] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * s_win[i + 1] : T(0);
       }
-      warp_fft1024<T, false, false>(re, im, xt, s_tw, lane);
-      __syncwarp();
-      float* s_mag = reinterpret_cast<float*>(xt);  // transpose tile is dead: |S| of this frame
+      warp_fft1024<T, false, false>(re, im, plane, s_tw, lane);
+      float* s_mag = reinterpret_cast<float*>(plane);  // transpose plane is dead: |S| of this frame
       const int partner = (32 - lane) & 31;
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
@@ -612,8 +718,9 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
 }
 
 template <typename T> SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max) {
-  return sizeof(typename cx_of<T>::type) * (size_t)(2048 + warps * XTILE_ELEMS) +
-         sizeof(T) * (size_t)round_up4(win) + sizeof(float) * (size_t)round_up4(span_max);
+  return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
+         sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win)) +
+         sizeof(float) * (size_t)round_up4(span_max);
 }
 
 }  // namespace sstts

@@ -135,6 +135,8 @@ static inline V __shfl_down_sync(unsigned m, V v, int delta) {
   return __shfl_sync(m, v, src < 32 ? src : lane);
 }
 
+static inline void sstts_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+static inline void sstts_cp_async_wait_all() {}
 template <typename V> static inline V __ldg(const V* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }

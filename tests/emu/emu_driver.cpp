@@ -42,7 +42,7 @@ template <typename T, bool INV, bool DIT>
 void fft_test_kernel(const T* in, T* out, const typename cx_of<T>::type* tw) {
   typedef typename cx_of<T>::type C;
   SSTTS_DYN_SMEM(smem);
-  C* xt = reinterpret_cast<C*>(smem);
+  T* xt = reinterpret_cast<T*>(smem);
   const int lane = threadIdx.x & 31;
   T re[32], im[32];
   for (int r = 0; r < 32; ++r) {
@@ -75,16 +75,20 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   A.tiles = H.tiles.data(); A.n_tiles = (int)H.tiles.size();
   A.tab = tabs.view(); A.mse_frame = nullptr;
   A.win = win; A.hop = hop; A.span_max = H.span_max;
-  const size_t smem = gl_step_smem_bytes<T>(W, win, H.span_max);
+  const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
-  emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true>(A); });
+  emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false>(A); });
   int cur = 0;
   for (int it = 0; it < n_iter; ++it) {
     A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
     A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
-    A.mse_frame = (it == n_iter - 1) ? mse_frame : nullptr;
-    emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false>(A); });
+    if (it == n_iter - 1 && mse_frame) {
+      A.mse_frame = mse_frame;
+      emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true>(A); });
+    } else {
+      emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false>(A); });
+    }
     cur ^= 1;
   }
   GLFinalArgs<T> F;
@@ -92,7 +96,7 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   F.frame_off = H.frame_off.data(); F.pad_off = H.pad_off.data(); F.sample_off = H.sample_off.data();
   F.tiles = H.tiles.data(); F.n_tiles = A.n_tiles; F.window = tabs.win.data(); F.wav_out = wav_out;
   F.win = win; F.hop = hop;
-  emu::launch(dim3(grid), dim3(256), sizeof(T) * win, [&]() { gl_finalize_kernel<T, G, 256>(F); });
+  emu::launch(dim3(grid), dim3(256), sizeof(T) * (round_up4(win) + round_up4(hop)), [&]() { gl_finalize_kernel<T, G, 256>(F); });
   return 0;
 }
 
@@ -145,13 +149,13 @@ int emu_fft1024(const double* in, double* out, int inverse, int prec) {
     HostTables<float> tabs; fill_tables<float>(1102, tabs);
     std::vector<float> fi(2048), fo(2048);
     for (int i = 0; i < 2048; ++i) fi[i] = (float)in[i];
-    const size_t smem = sizeof(float2) * XTILE_ELEMS;
+    const size_t smem = sizeof(float) * XPLANE_ELEMS;
     if (!inverse) emu::launch(dim3(1), dim3(32), smem, [&]() { fft_test_kernel<float, false, false>(fi.data(), fo.data(), tabs.tw.data()); });
     else emu::launch(dim3(1), dim3(32), smem, [&]() { fft_test_kernel<float, true, true>(fi.data(), fo.data(), tabs.tw.data()); });
     for (int i = 0; i < 2048; ++i) out[i] = fo[i];
   } else {
     HostTables<double> tabs; fill_tables<double>(1102, tabs);
-    const size_t smem = sizeof(double2) * XTILE_ELEMS;
+    const size_t smem = sizeof(double) * XPLANE_ELEMS;
     if (!inverse) emu::launch(dim3(1), dim3(32), smem, [&]() { fft_test_kernel<double, false, false>(in, out, tabs.tw.data()); });
     else emu::launch(dim3(1), dim3(32), smem, [&]() { fft_test_kernel<double, true, true>(in, out, tabs.tw.data()); });
   }
@@ -162,9 +166,9 @@ int emu_griffin_lim(int win, int hop, int prec, int n_utts, const long long* fra
                     const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap) {
   const bool model = (win == 1102 && hop == 275);
   if (prec == 1)
-    return model ? emu_gl_run<double, StaticGeom<1102, 275>, 4>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap)
-                 : emu_gl_run<double, DynGeom, 4>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap);
-  return model ? emu_gl_run<float, StaticGeom<1102, 275>, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap)
+    return model ? emu_gl_run<double, StaticGeom<1102, 275, 2048>, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap)
+                 : emu_gl_run<double, DynGeom, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap);
+  return model ? emu_gl_run<float, StaticGeom<1102, 275, 2048>, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap)
                : emu_gl_run<float, DynGeom, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap);
 }
 
@@ -176,9 +180,9 @@ int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels,
   const bool stats = (n_fft == 1024 && win == 1024 && hop == 256);
 #define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap
   if (prec == 1) {
-    if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, 4>(FEAT_ARGS);
-    if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, 4>(FEAT_ARGS);
-    return emu_feat_run<double, DynGeom, 4>(FEAT_ARGS);
+    if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
+    if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
+    return emu_feat_run<double, DynGeom, kWarps>(FEAT_ARGS);
   }
   if (model) return emu_feat_run<float, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
   if (stats) return emu_feat_run<float, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
