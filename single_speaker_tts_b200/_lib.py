@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libsstts.so')
+# SSTTS_LIB selects another build of the same library (kernel A/B experiments under tools/).
+LIB_PATH = os.environ.get('SSTTS_LIB') or os.path.join(_HERE, 'csrc', 'libsstts.so')
 
 SSTTS_F32 = 0
 SSTTS_F64 = 1

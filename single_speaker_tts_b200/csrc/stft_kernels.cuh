@@ -110,18 +110,21 @@ SSTTS_D void fill_interior_rwss(T* s_rw, const T* s_win, int hop, int win, int t
       const T w = s_win[r + j * hop];
       acc += w * w;
     }
-    s_rw[r] = acc > T(SSTTS_F32_TINY) ? T(1) / acc : T(1);
+    // the partial-sum buffers hold n_fft x the true overlap-add sums: the 1/n_fft of the inverse
+    // transform is folded in here (an exact power-of-two scaling)
+    s_rw[r] = (acc > T(SSTTS_F32_TINY) ? T(1) / acc : T(1)) * T(1.0 / NFFT);
   }
 }
 
-// Overlap-add sum -> waveform sample at padded coordinate p (divide by the window sum where it
-// exceeds tiny, as librosa.istft does).
+// n_fft x overlap-add sum -> waveform sample at padded coordinate p (divide by the window sum
+// where it exceeds tiny, as librosa.istft does).
 template <typename T>
 SSTTS_D T normalise_ola(T v, int p, int n_frames, int hop, int win, int lpad, const T* s_win,
                         const T* s_rw) {
   const int x = p - lpad;
   if (x >= win - hop && x / hop <= n_frames - 1) return v * s_rw[x % hop];
   const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
+  v *= T(1.0 / NFFT);
   return wss > T(SSTTS_F32_TINY) ? v / wss : v;
 }
 
@@ -171,9 +174,9 @@ SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane) {
   const float* gal = g - mis;
   for (int c = c_lo + lane; c < c_hi; c += 32) sstts_cp_async16(dst + 4 * c, gal + 4 * c);
   const int head = 4 * c_lo - mis;                     // elements [0, head)
-  if (lane < head) dst[lane + mis] = g[lane];
+  if (lane < head) sstts_cp_async4(dst + lane + mis, g + lane);
   const int tail0 = 4 * c_hi - mis;                    // elements [tail0, NBINS)
-  if (tail0 + lane < NBINS) dst[tail0 + lane + mis] = g[tail0 + lane];
+  if (tail0 + lane < NBINS) sstts_cp_async4(dst + tail0 + lane + mis, g + tail0 + lane);
   return mis;
 }
 
@@ -313,8 +316,6 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
   __syncthreads();
 
-  const T syn_scale = T(1.0 / NFFT);
-
   // Stage the analysis input of a tile: x_pad[span] = y_norm[reflect], y_norm = OLA sum / wss.
   auto stage = [&](int tile) {
     const GLTile tl = A.tiles[tile];
@@ -408,8 +409,8 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         const int m = 64 * n1 + 2 * lane;
         const int i = m - lpad;
         if (m >= mlo && m < lpad + win + 1) {
-          const T v0 = (i >= 0 && i < win) ? re[n1] * (s_win[i] * syn_scale) : T(0);
-          const T v1 = (i + 1 >= 0 && i + 1 < win) ? im[n1] * (s_win[i + 1] * syn_scale) : T(0);
+          const T v0 = (i >= 0 && i < win) ? re[n1] * s_win[i] : T(0);
+          const T v1 = (i + 1 >= 0 && i + 1 < win) ? im[n1] * s_win[i + 1] : T(0);
           plane[m - mlo] = v0;
           plane[m - mlo + 1] = v1;
         }

@@ -44,6 +44,10 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+// Blackwell packed FP32x2 intrinsics, emulated lane by lane (same IEEE results).
+static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace emu {
@@ -136,7 +140,10 @@ static inline V __shfl_down_sync(unsigned m, V v, int delta) {
 }
 
 static inline void sstts_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+static inline void sstts_cp_async4(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
 static inline void sstts_cp_async_wait_all() {}
+static inline void sstts_cp_async_commit() {}
+static inline void sstts_cp_async_wait_group1() {}
 template <typename V> static inline V __ldg(const V* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
