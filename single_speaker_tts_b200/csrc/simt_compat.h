@@ -30,6 +30,13 @@ __device__ __forceinline__ void sstts_cp_async_commit() {
 __device__ __forceinline__ void sstts_cp_async_wait_group1() {
   asm volatile("cp.async.wait_group 1;\n" ::: "memory");
 }
+// SFU log2 (MUFU.LG2) and square root (MUFU.SQRT), max relative error ~2^-22
+__device__ __forceinline__ float sstts_log2_approx(float x) { return __log2f(x); }
+__device__ __forceinline__ float sstts_sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void sstts_cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }

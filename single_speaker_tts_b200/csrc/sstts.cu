@@ -322,6 +322,7 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   A.tab = tables_view<T>(P->tab);
   A.mel_ptr = P->d_mel_ptr; A.mel_k0 = P->d_mel_k0; A.mel_w = reinterpret_cast<const T*>(P->d_mel_w);
   A.n_mels = P->cfg.n_mels;
+  A.mel_nnz = (int)P->mel.w.size();
   A.spec_out = reinterpret_cast<float2*>(O->spec_dev);
   A.lin_out = O->lin_db_dev;
   A.mel_out = O->mel_db_dev;
@@ -338,7 +339,7 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   A.n_fft = P->cfg.n_fft;
   if (A.n_mels < 1) { A.mel_out = nullptr; A.melraw_out = nullptr; }
 
-  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max);
+  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max, P->cfg.n_mels, (int)P->mel.w.size());
   int occ = 0, rc;
   if ((rc = configure_kernel(stft_feature_kernel<T, G, W>, W * 32, smem, &occ))) return rc;
   const int n_sms = P->n_sms > 0 ? P->n_sms : 148;

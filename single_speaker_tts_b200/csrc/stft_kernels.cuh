@@ -512,7 +512,7 @@ template <typename T> struct FeatArgs {
   const int* mel_ptr;             // [n_mels + 1] CSR row pointers
   const int* mel_k0;              // [n_mels]     first FFT bin of each mel filter
   const T* mel_w;                 // [nnz]        filter weights (float64 -> T)
-  int n_mels;
+  int n_mels, mel_nnz;
   float2* spec_out;               // (rows, 1025) complex64 STFT, or nullptr
   float* lin_out;                 // (rows, 1025) linear dB (normalised if normalize), or nullptr
   float* mel_out;                 // (rows, n_mels) mel dB (normalised if normalize), or nullptr
@@ -537,20 +537,11 @@ SSTTS_D long long encode_ordered(double v) {
   return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
 }
 
-template <typename T> struct feat_math;
-template <> struct feat_math<float> {
-  // |complex64| and 20 log10(max(1e-5, .)) in float32 (audio/conversion.py:29 on float32 input).
-  static SSTTS_D float magnitude(float xr, float xi) { return sqrtf(xr * xr + xi * xi); }
-  static SSTTS_D float mel_db(float m) { return 20.0f * log10f(fmaxf(1e-5f, m)); }
-};
-template <> struct feat_math<double> {
-  // float64 transform rounded to complex64 like librosa's stft_matrix, then |.| in float32.
-  static SSTTS_D float magnitude(double xr, double xi) {
-    const double fr = (double)(float)xr, fi = (double)(float)xi;
-    return (float)sqrt(fr * fr + fi * fi);
-  }
-  static SSTTS_D double mel_db(double m) { return 20.0 * log10(fmax(1e-5, m)); }
-};
+// dB epilogue constants: 20 log10(x) = kDbPerLog2Mag * log2(x); on |X|^2 it is half of that.
+// log2 / sqrt use the SFU approximations (MUFU.LG2 / MUFU.SQRT, ~1e-7 relative): their error is
+// ~2e-6 dB, four orders of magnitude inside the 1e-4 normalised tolerance (1e-4 * 135 dB).
+#define kDbPerLog2Mag 6.020599913279624f
+#define kDbPerLog2Pow 3.010299956639812f
 
 constexpr int FEAT_PLANE_ELEMS = 1056;  // >= XPLANE_ELEMS and >= NBINS floats
 
@@ -576,29 +567,59 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
   __syncthreads();
 
+  // mel filterbank (CSR) in shared memory, after the sample span
+  T* s_mel_w = reinterpret_cast<T*>(s_x + 2 * round_up4(A.span_max));
+  int* s_mel_ptr = reinterpret_cast<int*>(s_mel_w + round_up4(A.mel_nnz));
+  int* s_mel_k0 = s_mel_ptr + round_up4(A.n_mels + 1);
+  for (int i = tid; i < A.mel_nnz; i += NT) s_mel_w[i] = A.mel_w[i];
+  for (int i = tid; i < A.n_mels; i += NT) { s_mel_ptr[i] = A.mel_ptr[i]; s_mel_k0[i] = A.mel_k0[i]; }
+  if (tid == 0 && A.n_mels > 0) s_mel_ptr[A.n_mels] = A.mel_ptr[A.n_mels];
+  __syncthreads();
+
   T* plane = s_planes + warp * FEAT_PLANE_ELEMS;
   const bool want_lin = A.lin_out != nullptr;
-  const bool want_mel = (A.mel_out != nullptr) || (A.melraw_out != nullptr) ||
-                        (A.minmax_out != nullptr);
+  const bool want_lin_db = want_lin || (A.minmax_out != nullptr);
+  const bool want_mel = (A.n_mels > 0) && ((A.mel_out != nullptr) || (A.melraw_out != nullptr) ||
+                                           (A.minmax_out != nullptr));
+  // audio/conversion.py:78  clip(1 + (db - ref) / range, 0, 1) as one fma: db * scale + shift
+  const float lin_scale = 1.0f / A.lin_range_db, lin_shift = 1.0f - A.lin_ref_db / A.lin_range_db;
+  const float mel_scale = (float)(1.0 / A.mel_range_db), mel_shift = (float)(1.0 - A.mel_ref_db / A.mel_range_db);
+  const int pmode = A.mel_power == 1.0f ? 0 : (A.mel_power == 2.0f ? 1 : 2);
+
+  // Sample spans are staged with 4-byte LDGSTS (reflect padding resolved per element) into a
+  // double buffer: the span of the NEXT tile is in flight while the current tile is transformed.
+  float* s_xbuf[2] = {s_x, s_x + round_up4(A.span_max)};
+  auto issue_stage = [&](int t, float* buf) {
+    const FeatTile tl = A.tiles[t];
+    const long long soff = A.sample_off[tl.clip];
+    const int n_samples = (int)(A.sample_off[tl.clip + 1] - soff);
+    const int span_lo = tl.a * hop + lpad;
+    const int span = (tl.b - tl.a - 1) * hop + win;
+    const float* x = A.wav + soff;
+    for (int s = tid; s < span; s += NT) {
+      int q = span_lo + s - cpad;
+      if (q < 0 || q >= n_samples) q = reflect_index(q, n_samples);
+      sstts_cp_async4(buf + s, x + q);
+    }
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < A.n_tiles) issue_stage(blockIdx.x, s_xbuf[0]);
+  sstts_cp_async_commit();
 
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
     const FeatTile tl = A.tiles[tile];
-    const long long soff = A.sample_off[tl.clip];
-    const int n_samples = (int)(A.sample_off[tl.clip + 1] - soff);
     const long long f0 = A.frame_off[tl.clip];
     const int n_frames = (int)(A.frame_off[tl.clip + 1] - f0);
     const long long r0 = A.row_off[tl.clip];
     const int n_rows = (int)(A.row_off[tl.clip + 1] - r0);
     const int a = tl.a, b = tl.b, FT = b - a;
-    const int span_lo = a * hop + lpad;
-    const int span = (FT - 1) * hop + win;
-    const float* x = A.wav + soff;
+    const float* s_xc = s_xbuf[cur];
 
-    for (int s = tid; s < span; s += NT) {
-      int q = span_lo + s - cpad;
-      if (q < 0 || q >= n_samples) q = reflect_index(q, n_samples);
-      s_x[s] = x[q];
-    }
+    sstts_cp_async_wait_all();    // this thread's part of the current span has landed
+    __syncthreads();              // ... everyone's has, and the other buffer is no longer read
+    if (tile + (int)gridDim.x < A.n_tiles) issue_stage(tile + gridDim.x, s_xbuf[cur ^ 1]);
+    sstts_cp_async_commit();
+    cur ^= 1;
     // zero rows appended by apply_reduction_padding (datasets/dataset_helper.py:383-393)
     if (tl.last && n_rows > n_frames) {
       const long long zr0 = r0 + n_frames;
@@ -606,13 +627,12 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
       if (A.lin_out) for (int i = tid; i < nz * n_bins; i += NT) A.lin_out[zr0 * n_bins + i] = 0.0f;
       if (A.mel_out) for (int i = tid; i < nz * A.n_mels; i += NT) A.mel_out[zr0 * A.n_mels + i] = 0.0f;
     }
-    __syncthreads();
 
-    double mn_lin = 1e300, mx_lin = -1e300, mn_mel = 1e300, mx_mel = -1e300;
+    float mn_lin = 3.0e38f, mx_lin = -3.0e38f, mn_mel = 3.0e38f, mx_mel = -3.0e38f;
     for (int jr = warp; jr < FT; jr += W) {
       const long long row = r0 + a + jr;
       T re[32], im[32];
-      const float* fin = s_x + jr * hop - lpad;
+      const float* fin = s_xc + jr * hop - lpad;
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) {
         const int m = 64 * n1 + 2 * lane;
@@ -642,58 +662,64 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
         const T xkr = T(0.5) * (er + wor), xki = T(0.5) * (ei + woi);   // X[k]
         const T xnr = T(0.5) * (er - wor), xni = T(0.5) * (woi - ei);   // X[N-k]
         if ((k & bmask) == 0) {   // kn = 1024 - k shares k's residue
+          // librosa stores the float64 transform as complex64; everything downstream is float32
+          const float fkr = (float)xkr, fki = (float)xki, fnr = (float)xnr, fni = (float)xni;
+          const int ko = k >> bshift, no = kn >> bshift;
           if (A.spec_out) {
-            A.spec_out[row * n_bins + (k >> bshift)] = make_float2((float)xkr, (float)xki);
-            A.spec_out[row * n_bins + (kn >> bshift)] = make_float2((float)xnr, (float)xni);
+            A.spec_out[row * n_bins + ko] = make_float2(fkr, fki);
+            A.spec_out[row * n_bins + no] = make_float2(fnr, fni);
           }
-          s_mag[k >> bshift] = feat_math<T>::magnitude(xkr, xki);
-          s_mag[kn >> bshift] = feat_math<T>::magnitude(xnr, xni);
+          const float pk = fmaf(fkr, fkr, fki * fki), pn = fmaf(fnr, fnr, fni * fni);   // |X|^2
+          if (want_mel) { s_mag[ko] = sstts_sqrt_approx(pk); s_mag[no] = sstts_sqrt_approx(pn); }
+          if (want_lin_db) {
+            // 20 log10(max(1e-5, |X|)) = 10 log10(2) log2(max(1e-10, |X|^2))   (conversion.py:29)
+            const float dk = kDbPerLog2Pow * sstts_log2_approx(fmaxf(1e-10f, pk));
+            const float dn = kDbPerLog2Pow * sstts_log2_approx(fmaxf(1e-10f, pn));
+            mn_lin = fminf(mn_lin, fminf(dk, dn));
+            mx_lin = fmaxf(mx_lin, fmaxf(dk, dn));
+            if (want_lin) {
+              A.lin_out[row * n_bins + ko] = A.normalize ? fminf(fmaxf(fmaf(dk, lin_scale, lin_shift), 0.0f), 1.0f) : dk;
+              A.lin_out[row * n_bins + no] = A.normalize ? fminf(fmaxf(fmaf(dn, lin_scale, lin_shift), 0.0f), 1.0f) : dn;
+            }
+          }
         }
       }
-      if (lane == 0) {
+      if (lane == 0) {   // k = 512: X = conj(Z)
         const int sl = brev5(16);
         const int kh = (HALF / 2) >> bshift;
-        if (A.spec_out) A.spec_out[row * n_bins + kh] = make_float2((float)re[sl], (float)(-im[sl]));
-        s_mag[kh] = feat_math<T>::magnitude(re[sl], -im[sl]);
-      }
-      __syncwarp();
-      if (want_lin || A.minmax_out) {
-        for (int k = lane; k < n_bins; k += 32) {
-          const float db = 20.0f * log10f(fmaxf(1e-5f, s_mag[k]));
-          mn_lin = fmin(mn_lin, (double)db);
-          mx_lin = fmax(mx_lin, (double)db);
-          if (want_lin) {
-            float v = db;
-            if (A.normalize) {
-              v = 1.0f + (db - A.lin_ref_db) / A.lin_range_db;
-              v = fminf(fmaxf(v, 0.0f), 1.0f);
-            }
-            A.lin_out[row * n_bins + k] = v;
-          }
+        const float fr = (float)re[sl], fi = -(float)im[sl];
+        if (A.spec_out) A.spec_out[row * n_bins + kh] = make_float2(fr, fi);
+        const float ph = fmaf(fr, fr, fi * fi);
+        if (want_mel) s_mag[kh] = sstts_sqrt_approx(ph);
+        if (want_lin_db) {
+          const float dh = kDbPerLog2Pow * sstts_log2_approx(fmaxf(1e-10f, ph));
+          mn_lin = fminf(mn_lin, dh);
+          mx_lin = fmaxf(mx_lin, dh);
+          if (want_lin) A.lin_out[row * n_bins + kh] = A.normalize ? fminf(fmaxf(fmaf(dh, lin_scale, lin_shift), 0.0f), 1.0f) : dh;
         }
       }
+      __syncwarp();
       if (want_mel) {
+        // mel_basis @ |S| ** power: one filter per lane and pass; filters are contiguous runs of
+        // FFT bins (CSR staged in shared memory); accumulation in T (float64 in the exact mode,
+        // like the reference's float64 np.dot, audio/features.py:84)
         for (int m = lane; m < A.n_mels; m += 32) {
-          const int p0 = A.mel_ptr[m], p1 = A.mel_ptr[m + 1];
-          const float* mg = s_mag + A.mel_k0[m];
+          const int p0 = s_mel_ptr[m], p1 = s_mel_ptr[m + 1];
+          const float* mg = s_mag + s_mel_k0[m] - p0;
           T acc = T(0);
-          for (int i = p0; i < p1; ++i) {
-            float sm = mg[i - p0];
-            if (A.mel_power != 1.0f) sm = (A.mel_power == 2.0f) ? sm * sm : powf(sm, A.mel_power);
-            acc += A.mel_w[i] * (T)sm;
+          if (pmode == 0) {
+            for (int i = p0; i < p1; ++i) acc += s_mel_w[i] * (T)mg[i];
+          } else if (pmode == 1) {
+            for (int i = p0; i < p1; ++i) acc += s_mel_w[i] * (T)(mg[i] * mg[i]);
+          } else {
+            for (int i = p0; i < p1; ++i) acc += s_mel_w[i] * (T)powf(mg[i], A.mel_power);
           }
           if (A.melraw_out) A.melraw_out[row * A.n_mels + m] = (double)acc;
-          const T db = feat_math<T>::mel_db(acc < T(0) ? -acc : acc);
-          mn_mel = fmin(mn_mel, (double)db);
-          mx_mel = fmax(mx_mel, (double)db);
-          if (A.mel_out) {
-            T v = db;
-            if (A.normalize) {
-              v = T(1) + (db - (T)A.mel_ref_db) / (T)A.mel_range_db;
-              v = v < T(0) ? T(0) : (v > T(1) ? T(1) : v);
-            }
-            A.mel_out[row * A.n_mels + m] = (float)v;
-          }
+          const float db = kDbPerLog2Mag * sstts_log2_approx(fmaxf(1e-5f, fabsf((float)acc)));
+          mn_mel = fminf(mn_mel, db);
+          mx_mel = fmaxf(mx_mel, db);
+          if (A.mel_out)
+            A.mel_out[row * A.n_mels + m] = A.normalize ? fminf(fmaxf(fmaf(db, mel_scale, mel_shift), 0.0f), 1.0f) : db;
         }
       }
       __syncwarp();
@@ -701,27 +727,29 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
     if (A.minmax_out) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        mn_lin = fmin(mn_lin, __shfl_xor_sync(0xffffffffu, mn_lin, o));
-        mx_lin = fmax(mx_lin, __shfl_xor_sync(0xffffffffu, mx_lin, o));
-        mn_mel = fmin(mn_mel, __shfl_xor_sync(0xffffffffu, mn_mel, o));
-        mx_mel = fmax(mx_mel, __shfl_xor_sync(0xffffffffu, mx_mel, o));
+        mn_lin = fminf(mn_lin, __shfl_xor_sync(0xffffffffu, mn_lin, o));
+        mx_lin = fmaxf(mx_lin, __shfl_xor_sync(0xffffffffu, mx_lin, o));
+        mn_mel = fminf(mn_mel, __shfl_xor_sync(0xffffffffu, mn_mel, o));
+        mx_mel = fmaxf(mx_mel, __shfl_xor_sync(0xffffffffu, mx_mel, o));
       }
       if (lane == 0 && warp < FT) {
         long long* mm = A.minmax_out + 4LL * tl.clip;
-        atomicMin(mm + 0, encode_ordered(mn_lin));
-        atomicMax(mm + 1, encode_ordered(mx_lin));
-        atomicMin(mm + 2, encode_ordered(mn_mel));
-        atomicMax(mm + 3, encode_ordered(mx_mel));
+        atomicMin(mm + 0, encode_ordered((double)mn_lin));
+        atomicMax(mm + 1, encode_ordered((double)mx_lin));
+        atomicMin(mm + 2, encode_ordered((double)mn_mel));
+        atomicMax(mm + 3, encode_ordered((double)mx_mel));
       }
     }
-    __syncthreads();
+    // no barrier here: the one at the top of the next iteration orders the buffer hand-over
   }
 }
 
-template <typename T> SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max) {
+template <typename T>
+SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_mels, int mel_nnz) {
   return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
          sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win)) +
-         sizeof(float) * (size_t)round_up4(span_max);
+         sizeof(float) * 2 * (size_t)round_up4(span_max) + sizeof(T) * (size_t)round_up4(mel_nnz) +
+         sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
 }
 
 }  // namespace sstts

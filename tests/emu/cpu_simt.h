@@ -142,6 +142,8 @@ static inline V __shfl_down_sync(unsigned m, V v, int delta) {
 static inline void sstts_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
 static inline void sstts_cp_async4(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
 static inline void sstts_cp_async_wait_all() {}
+static inline float sstts_sqrt_approx(float x) { return sqrtf(x); }
+static inline float sstts_log2_approx(float x) { return log2f(x); }
 static inline void sstts_cp_async_commit() {}
 static inline void sstts_cp_async_wait_group1() {}
 template <typename V> static inline V __ldg(const V* p) { return *p; }

@@ -121,7 +121,7 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   A.wav = wav; A.sample_off = H.sample_off.data(); A.frame_off = H.frame_off.data();
   A.row_off = H.row_off.data(); A.tiles = H.tiles.data(); A.n_tiles = (int)H.tiles.size();
   A.tab = tabs.view();
-  A.mel_ptr = M.ptr.data(); A.mel_k0 = M.k0.data(); A.mel_w = mw.data(); A.n_mels = n_mels;
+  A.mel_ptr = M.ptr.data(); A.mel_k0 = M.k0.data(); A.mel_w = mw.data(); A.n_mels = n_mels; A.mel_nnz = (int)mw.size();
   A.spec_out = reinterpret_cast<float2*>(spec); A.lin_out = lin; A.mel_out = mel; A.melraw_out = melraw;
   A.minmax_out = minmax ? mm.data() : nullptr;
   A.lin_ref_db = (float)lin_ref; A.lin_range_db = (float)(fabs(lin_ref) + fabs(lin_max));
@@ -129,7 +129,7 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   A.mel_power = (float)power; A.normalize = normalize;
   A.win = win; A.hop = hop; A.span_max = H.span_max; A.n_fft = n_fft;
   if (minmax) for (size_t i = 0; i < mm.size(); ++i) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
-  const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max);
+  const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max, n_mels, (int)mw.size());
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
   emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { stft_feature_kernel<T, G, W>(A); });
   if (minmax) for (size_t i = 0; i < mm.size(); ++i) {
