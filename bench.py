@@ -378,6 +378,136 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[3] / configs[4]: sharded multi-GPU workloads (torchrun, one rank per GPU)
+# ------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    return torch, dist, rank, world, dev
+
+
+def run_corpus(args):
+    """configs[3]: corpus pass over 13,100 synthetic LJSpeech-length clips sharded by clip:
+    (1) per-clip dB statistics (n_fft 1024 / hop 256) + one all-reduce -> corpus constants,
+    (2) feature pre-calculation (2048 / 275 / 1102, reduction 5) with those constants.
+    Host numpy in, host numpy out (pinned staging); strong scaling (fixed total work)."""
+    torch, dist, rank, world, dev = _dist_setup()
+    from single_speaker_tts_b200 import distributed
+    from single_speaker_tts_b200.audio.features import features_batch
+    from single_speaker_tts_b200.synthetic import ClipPlan
+    n_total = args.clips or 13100
+    plan = ClipPlan(n_total, seed=3, kind='ljspeech', pool=32)
+    shards = distributed.shard_by_cost(plan.frames(HOP), world)
+    mine = shards[rank]
+    wavs = plan.clips(mine)
+    audio_total = float(plan.lengths.sum()) / SR
+
+    def one_pass():
+        mean4, mn4, mx4, _ = distributed.corpus_decibel_statistics(wavs, mine, n_total, SR, batch_clips=512)
+        lin_max, lin_ref, mel_max, mel_ref = mean4          # tacotron/dataset_statistics.py:35-39
+        n_rows = 0
+        for s in range(0, len(wavs), 256):
+            feats = features_batch(wavs[s:s + 256], NFFT, HOP, WIN, SR, 80, 0, 8000,
+                                   lin_ref, lin_max, mel_ref, mel_max, reduction=5)
+            n_rows += sum(m.shape[0] for m, _ in feats)
+        return mean4, n_rows
+
+    for _ in range(max(1, args.warmup)):
+        one_pass()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mean4, n_rows = one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'corpus_pass_audio_sec_per_sec', 'value': audio_total * args.steps / (ms / 1000.0),
+            'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[3]: statistics (1024/256) + all-reduce + feature precalc '
+                                   '(2048/275/1102, r=5) over %d LJSpeech-length clips, end to end' % n_total,
+                       'sharding': 'by clip, balanced by frames; one all-reduce of the (n_clips, 4) table'},
+            'corpus_statistics': {'linear_mag_max_db': mean4[0], 'linear_ref_db': mean4[1],
+                                  'mel_mag_max_db': mean4[2], 'mel_mag_ref_db': mean4[3]},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_gl_sharded(args):
+    """configs[4]: Griffin-Lim, 100 iterations, 4,096 ragged utterances sharded by utterance
+    (no collective), end to end through spectrograms_to_wavs; strong scaling."""
+    torch, dist, rank, world, dev = _dist_setup()
+    from single_speaker_tts_b200 import _runtime, distributed
+    from single_speaker_tts_b200.audio import synthesis
+    from single_speaker_tts_b200.synthetic import ClipPlan
+    n_total = args.clips or 4096
+    n_iter = 100
+    plan = ClipPlan(n_total, seed=4, kind='uniform', pool=32)
+    frames = plan.frames(HOP)
+    mine = distributed.shard_by_cost(frames, world)[rank]
+    audio_total = float((HOP * (frames - 1)).sum()) / SR
+    mags = []
+    for s in range(0, len(mine), 256):       # |STFT| of this rank's clips via the feature kernel
+        idx = mine[s:s + 256]
+        fb = _runtime.stft_features_batch(plan.clips(idx), NFFT, HOP, WIN, want_spec=True, precision='f64')
+        for i in range(len(idx)):
+            mags.append(np.abs(fb.rows(fb.spec, i)).T)
+
+    def one_pass():
+        for s in range(0, len(mags), 512):
+            synthesis.spectrograms_to_wavs(mags[s:s + 512], WIN, HOP, NFFT, n_iter, seed=1234 + s)
+
+    for _ in range(max(1, args.warmup)):
+        one_pass()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'griffin_lim_100it_audio_sec_per_sec', 'value': audio_total * args.steps / (ms / 1000.0),
+            'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[4]: Griffin-Lim 100 it over %d ragged utterances, '
+                                   'end to end (host numpy in / out)' % n_total,
+                       'sharding': 'by utterance, balanced by frames; no collective'},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -385,9 +515,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='gl256', choices=['gl256', 'corpus', 'gl4096'],
+                    help='gl256 = configs[1]+[2] (default, the driver contract); corpus = configs[3]; gl4096 = configs[4]')
+    ap.add_argument('--clips', type=int, default=0, help='override the clip count of corpus / gl4096')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'corpus':
+        run_corpus(args)
+    elif args.workload == 'gl4096':
+        run_gl_sharded(args)
     else:
         run_ours(args)
 

@@ -78,3 +78,29 @@ def make_clips(n_clips, seed, kind='uniform', pool=None, sr=SAMPLING_RATE):
         start = int(rng.integers(0, base_len - n + 1))
         clips.append(np.ascontiguousarray(b[start:start + n]))
     return clips
+
+
+class ClipPlan:
+    """Deterministic description of a large synthetic corpus: ``n_clips`` ragged clips, each a
+    seeded crop of one of ``pool`` base clips.  Every rank builds the same plan (cheap: no audio
+    is synthesised per clip) and materialises only the clips of its own shard."""
+
+    def __init__(self, n_clips, seed, kind='ljspeech', pool=32, sr=SAMPLING_RATE):
+        rng = np.random.default_rng(seed)
+        self.sr = sr
+        self.lengths = ragged_durations(n_clips, rng, kind=kind, sr=sr)
+        base_len = int(10.2 * sr)
+        self.bases = [speech_like_clip(base_len, rng, sr=sr) for _ in range(int(pool))]
+        self.base_id = rng.integers(0, len(self.bases), n_clips)
+        self.start = (rng.random(n_clips) * (base_len - self.lengths + 1)).astype(np.int64)
+
+    def frames(self, hop):
+        return 1 + self.lengths // hop
+
+    def clip(self, i):
+        b = self.bases[int(self.base_id[i])]
+        s = int(self.start[i])
+        return b[s:s + int(self.lengths[i])]
+
+    def clips(self, indices):
+        return [self.clip(i) for i in indices]
