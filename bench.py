@@ -50,6 +50,17 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel` from the committed ncu
+    --set full capture of this workload shape (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f)[kernel]['dram_bytes_per_launch']
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle sampling during the timed region."""
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
@@ -318,7 +329,9 @@ def run_ours(args):
             'value': sum_over_ranks(audio_in_s) / (per_launch_ms / 1000.0), 'unit': 'audio-s/s',
             'ms_per_step': per_launch_ms,
             'roofline': {'bound': 'hbm', 'achieved': alg / (per_launch_ms / 1000.0) / 1e9, 'peak': peak_gbs,
-                         'unit': 'GB/s', 'frac': alg / (per_launch_ms / 1000.0) / 1e9 / peak_gbs, 'traffic': None},
+                         'unit': 'GB/s', 'frac': alg / (per_launch_ms / 1000.0) / 1e9 / peak_gbs,
+                         'traffic': measured_traffic('stft_feature_kernel<%s, StaticGeom<1102, 275, 2048>, 8>'
+                                                     % ('double' if prec == 'f64' else 'float'))},
         }
         lib.sstts_feat_plan_destroy(fplan)
         del lin, mel, wav_in
@@ -361,7 +374,9 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h, 'ms_per_step': gl_e2e_ms / e2e_steps},
             'gpu_launches': args.steps * (GL_ITERS + 3),
             'roofline': {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',
-                         'frac': gl_achieved / peak_gbs, 'traffic': None, 'kernel': 'gl_step_kernel',
+                         'frac': gl_achieved / peak_gbs,
+                         'traffic': measured_traffic('gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>'),
+                         'kernel': 'gl_step_kernel',
                          'peak_source': peak_src, 'ms_per_launch': iter_ms,
                          'algorithmic_bytes_per_launch': gl_alg_bytes,
                          'how': '(CUDA-event time of the 50-iteration call - same call with 0 iterations) / 50'},

@@ -15,7 +15,7 @@ from single_speaker_tts_b200 import _lib, _runtime, distributed
 from single_speaker_tts_b200.audio import conversion, effects
 from single_speaker_tts_b200.datasets.dataset_helper import DatasetHelper, LJSpeechDatasetHelper
 from single_speaker_tts_b200.datasets.statistics import reduce_decibel_statistics
-from single_speaker_tts_b200.synthetic import make_clips, speech_like_clip
+from single_speaker_tts_b200.synthetic import ClipPlan, make_clips, speech_like_clip
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -121,3 +121,28 @@ def test_synthetic_clips_are_seeded_and_shaped():
     assert all(x.dtype == np.float32 and 22050 <= len(x) <= 220500 and abs(np.abs(x).max() - 0.5) < 1e-6 for x in a)
     c = make_clips(6, seed=2, kind='ljspeech', pool=2)
     assert all(int(1.11 * 22050) <= len(x) <= int(10.1 * 22050) + 1 for x in c)
+
+
+def test_clip_plan_is_identical_on_every_rank():
+    a = ClipPlan(50, seed=3, kind='ljspeech', pool=2)
+    b = ClipPlan(50, seed=3, kind='ljspeech', pool=2)
+    assert np.array_equal(a.lengths, b.lengths) and np.array_equal(a.start, b.start)
+    for i in (0, 17, 49):
+        assert np.array_equal(a.clip(i), b.clip(i)) and len(a.clip(i)) == a.lengths[i]
+    assert np.array_equal(a.frames(275), 1 + a.lengths // 275)
+    shards = distributed.shard_by_cost(a.frames(275), 4)
+    assert sorted(i for s in shards for i in s) == list(range(50))
+
+
+def test_bench_reference_arm_line_shape():
+    """bench.py --impl reference prints one JSON line with the contract keys (tiny run)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, env=env, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
+    d = json.loads(line)
+    assert d['impl'] == 'reference' and d['unit'] == 'audio-s/s' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
