@@ -45,9 +45,9 @@ typedef enum sstts_precision {
 /* STFT geometry + mel filterbank.  Mirrors the arguments the reference threads through
  * audio/features.py:5-6,116 and audio/synthesis.py:43 (values: tacotron/params/model.py:13-33). */
 typedef struct sstts_stft_config {
-  int n_fft;         /* 2048 (the only transform size built so far) */
+  int n_fft;         /* Griffin-Lim: 2048.  Features: 2048, 1024 or 512 */
   int win_length;    /* <= n_fft, n_fft - win_length even; periodic Hann, zero-padded centred */
-  int hop_length;    /* win_length / hop_length <= 8 for Griffin-Lim */
+  int hop_length;    /* ceil(win_length / hop_length) <= 5 for Griffin-Lim */
   int sampling_rate; /* mel filterbank only */
   int n_mels;        /* 0: no filterbank */
   double mel_fmin;
@@ -95,6 +95,15 @@ int sstts_griffin_lim(const sstts_gl_plan* plan, const float* mag_dev, const flo
  * (batched extension: replaces the host-side np.random.rand of audio/synthesis.py:85). */
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream);
 
+/* Call-site glue in front of Griffin-Lim -- replaces tacotron/inference.py:94-101,175 (and
+ * tacotron/serve.py:42-59): audio/conversion.py:81-102 `inv_normalize_decibel`, :32-53
+ * `decibel_to_magnitude` and `np.power(mag, magnitude_power)` fused into one pass over the model
+ * output.  norm_dev / mag_out_dev: n float32 values (frame-major (sum T, bins), same layout in and
+ * out; may alias).  *flag_dev (optional int, caller-zeroed) is set to 1 if any dB value is below
+ * -100, where the reference raises AssertionError (audio/conversion.py:47-49). */
+int sstts_denormalize_magnitude(const float* norm_dev, int64_t n, double ref_db, double max_db,
+                                double power, float* mag_out_dev, int* flag_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * STFT features -- replaces audio/features.py:116-145 `linear_scale_spectrogram`, :5-86
  * `mel_scale_spectrogram`, audio/conversion.py:5-29 `magnitude_to_decibel`, :56-78
@@ -108,6 +117,10 @@ typedef struct sstts_feat_plan sstts_feat_plan;
  * rows to a multiple of r (datasets/dataset_helper.py:357-401). */
 int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int64_t* sample_off_host,
                            int reduction, sstts_feat_plan** plan_out);
+/* Same, for clips that are not packed back to back: clip c occupies
+ * wav_dev[clip_start[c] .. clip_start[c] + clip_len[c]) (e.g. the trimmed part of an untrimmed upload). */
+int sstts_feat_plan_create_ranges(const sstts_stft_config* cfg, int n_clips, const int64_t* clip_start_host,
+                                  const int64_t* clip_len_host, int reduction, sstts_feat_plan** plan_out);
 void sstts_feat_plan_destroy(sstts_feat_plan* plan);
 int64_t sstts_feat_total_frames(const sstts_feat_plan* plan);
 int64_t sstts_feat_total_rows(const sstts_feat_plan* plan);
@@ -132,6 +145,14 @@ typedef struct sstts_feat_outputs {
 
 int sstts_stft_features(const sstts_feat_plan* plan, const float* wav_dev,
                         const sstts_feat_outputs* out, void* stream);
+
+/* Silence trimming -- replaces `librosa.effects.trim(wav)` as called by datasets/lj_speech.py:119
+ * (top_db 60, frame_length 2048, hop_length 512; wrapper audio/effects.py:188-215).
+ * clip_start_dev / clip_len_dev: int64[n_clips] on the device; bounds_dev: int64[n_clips * 2]
+ * receives (start, end) relative to each clip, (0, 0) for an all-silent clip. */
+int sstts_trim_bounds(const float* wav_dev, int n_clips, const int64_t* clip_start_dev,
+                      const int64_t* clip_len_dev, double top_db, int frame_length, int hop_length,
+                      int64_t* bounds_dev, void* stream);
 
 #ifdef __cplusplus
 }

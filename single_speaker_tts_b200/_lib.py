@@ -55,8 +55,13 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p]),
     'sstts_random_phase': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p,
                                           ctypes.c_void_p]),
+    'sstts_denormalize_magnitude': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
+                                                   ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p]),
     'sstts_feat_plan_create': (ctypes.c_int, [ctypes.POINTER(StftConfig), ctypes.c_int, _c_i64_p,
                                               ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    'sstts_feat_plan_create_ranges': (ctypes.c_int, [ctypes.POINTER(StftConfig), ctypes.c_int, _c_i64_p, _c_i64_p,
+                                                     ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     'sstts_feat_plan_destroy': (None, [ctypes.c_void_p]),
     'sstts_feat_total_frames': (ctypes.c_int64, [ctypes.c_void_p]),
     'sstts_feat_total_rows': (ctypes.c_int64, [ctypes.c_void_p]),
@@ -65,6 +70,9 @@ SIGNATURES = {
     'sstts_feat_mel_basis': (_c_f64_p, [ctypes.c_void_p]),
     'sstts_stft_features': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.POINTER(FeatOutputs), ctypes.c_void_p]),
+    'sstts_trim_bounds': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
 }
 
 _lib = None

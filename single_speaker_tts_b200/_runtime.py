@@ -11,7 +11,7 @@ import threading
 import numpy as np
 import torch
 
-from . import _lib
+from . import _hostio, _lib
 from ._lib import SsttsError
 
 _PRECISIONS = {'f32': _lib.SSTTS_F32, 'f64': _lib.SSTTS_F64,
@@ -98,24 +98,11 @@ def _offsets(counts):
     return off
 
 
-def _pack_rows_pinned(blocks, width, dtype):
-    """Stack 2-D blocks (rows_i, width) into one pinned host tensor (sum rows, width)."""
-    rows = sum(b.shape[0] for b in blocks)
-    host = torch.empty((rows, width), dtype=dtype, pin_memory=True)
-    dst = host.numpy()
-    r = 0
-    for b in blocks:
-        n = b.shape[0]
-        np.copyto(dst[r:r + n], b, casting='unsafe')
-        r += n
-    return host
-
-
 # ----------------------------------------------------------------------------------------------
 # Griffin-Lim
 # ----------------------------------------------------------------------------------------------
 def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
-                      precision='f32', return_mse=False, device=None):
+                      precision='f32', return_mse=False, device=None, denormalize=None):
     """Griffin-Lim for a ragged batch (reference: audio/synthesis.py:43-125, one call per item).
 
     mags   : list of (1 + n_fft/2, T_i) magnitude spectrograms (any float dtype / layout).
@@ -123,6 +110,10 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
              ``np.exp(2j*pi*np.random.rand(...))``); if None they are generated on the device from
              ``seed`` (seed=None draws one 63-bit seed from numpy's global RNG, so
              ``np.random.seed`` still makes a run reproducible).
+    denormalize : None, or ``(ref_db, max_db, power)``: ``mags`` then holds the model's normalised
+             outputs in its own orientation ``(T_i, 1 + n_fft/2)`` and the glue of
+             tacotron/inference.py:94-101,175 (inv_normalize_decibel -> decibel_to_magnitude ->
+             ** power) runs fused on the device before the first iteration.
     Returns (list of float32 waveforms of length hop*(T_i-1), list of mse floats or None).
     """
     lib = _lib.load()
@@ -131,6 +122,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
     n = len(mags)
     if n == 0:
         return [], ([] if return_mse else None)
+    if denormalize is not None:
+        mags = [np.asarray(m).T for m in mags]      # (bins, T) views of the (T, bins) model outputs
     frames = []
     for m in mags:
         if m.ndim != 2 or m.shape[0] != n_bins:
@@ -158,8 +151,13 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
     sample_off = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(n + 1,)).copy()
 
     with torch.cuda.device(dev):
-        mag_host = _pack_rows_pinned([m.T for m in mags], n_bins, torch.float32)
-        mag_dev = mag_host.to(dev, non_blocking=True)
+        mag_dev = _hostio.upload_rows([m.T for m in mags], n_bins, torch.float32, dev, slot='mag')
+        flag_dev = None
+        if denormalize is not None:
+            ref_db, max_db, power = [float(v) for v in denormalize]
+            flag_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), total_frames * n_bins, ref_db, max_db,
+                                                       power, _ptr(mag_dev), _ptr(flag_dev), _stream_ptr()))
         if angles is not None:
             if len(angles) != n:
                 raise ValueError('need one initial phase array per spectrogram')
@@ -168,8 +166,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                 if a.shape != m.shape:
                     raise ValueError('initial phase shape {} != spectrogram shape {}'.format(a.shape, m.shape))
                 blocks.append(np.asarray(a).T)
-            ph_host = _pack_rows_pinned(blocks, n_bins, torch.complex64)
-            phase_dev = torch.view_as_real(ph_host.to(dev, non_blocking=True))
+            phase_dev = torch.view_as_real(_hostio.upload_rows(blocks, n_bins, torch.complex64, dev, slot='phase'))
         else:
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
@@ -181,15 +178,17 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         mse_dev = torch.zeros(total_frames, dtype=torch.float64, device=dev) if return_mse else None
         _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
                                          _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
-        wav_host = torch.empty(max(total_samples, 1), dtype=torch.float32, pin_memory=True)
-        wav_host.copy_(wav_dev, non_blocking=True)
-        mse_host = mse_dev.cpu() if return_mse else None
+        wav_np = _hostio.download(wav_dev)
+        mf = _hostio.download(mse_dev) if return_mse else None
+        flag = _hostio.download(flag_dev) if flag_dev is not None else None
         torch.cuda.current_stream().synchronize()
-    wav_np = wav_host.numpy()
+    if flag is not None and int(flag[0]) != 0:
+        # same error as the reference's decibel_to_magnitude (audio/conversion.py:47-49)
+        raise AssertionError('"conversion.decibel_to_magnitude" was asked to convert a dB value '
+                             'smaller -100 dB.')
     wavs = [wav_np[sample_off[i]:sample_off[i + 1]] for i in range(n)]
     mses = None
     if return_mse:
-        mf = mse_host.numpy()
         mses = []
         for i in range(n):
             if frames[i] < 2:
@@ -216,6 +215,7 @@ class FeatureBatch:
         self.mel_raw = None   # (rows, n_mels) float64
         self.minmax = None    # (n_clips, 4) float64
         self.mel_basis = None
+        self.trim_bounds = None  # (n_clips, 2) int64 (start, end) when trimming was requested
 
     def rows(self, arr, i, padded=False):
         a, b = int(self.row_off[i]), int(self.row_off[i + 1])
@@ -227,12 +227,15 @@ class FeatureBatch:
 def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None, n_mels=0, fmin=0.0,
                         fmax=None, reduction=1, want_spec=False, want_lin=False, want_mel=False,
                         want_mel_raw=False, want_minmax=False, normalize=None, power=1.0,
-                        precision='f64', device=None, keep_on_device=False):
+                        precision='f64', device=None, keep_on_device=False, trim=None):
     """Batched STFT -> |.| -> linear / mel -> dB -> (0,1) pipeline on the GPU.
 
     normalize: None (raw dB) or (lin_ref_db, lin_max_db, mel_ref_db, mel_max_db) as in
     audio/conversion.py:56-78.  Outputs are frame-major (rows, bins); with ``reduction`` r > 1 every
     clip's rows are zero-padded to a multiple of r (datasets/dataset_helper.py:357-401).
+    trim: None, or ``(top_db, frame_length, hop_length)``: silence-trim every clip on the device
+    first (librosa.effects.trim as called at datasets/lj_speech.py:119); the features are computed
+    on the trimmed part of the same upload and ``result.trim_bounds`` holds (start, end) per clip.
     """
     lib = _lib.load()
     dev = require_cuda(device)
@@ -255,15 +258,33 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     need_mel = want_mel or want_mel_raw or want_minmax
     cfg = _make_config(n_fft, win_length, hop_length, precision, sampling_rate if need_mel else 0,
                        n_mels if need_mel else 0, fmin, fmax)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    clip_start = np.ascontiguousarray(sample_off[:-1])
+    clip_len = np.asarray(lens, dtype=np.int64)
+    trim_bounds = None
+    with torch.cuda.device(dev):
+        wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav')
+        if trim is not None:
+            top_db, t_frame, t_hop = trim
+            start_dev = torch.from_numpy(clip_start).to(dev)
+            len_dev = torch.from_numpy(clip_len).to(dev)
+            bounds_dev = torch.empty((n, 2), dtype=torch.int64, device=dev)
+            _lib.check(lib.sstts_trim_bounds(_ptr(wav_dev), n, _ptr(start_dev), _ptr(len_dev), float(top_db),
+                                             int(t_frame), int(t_hop), _ptr(bounds_dev), _stream_ptr()))
+            trim_bounds = bounds_dev.cpu().numpy()
+            clip_start = clip_start + trim_bounds[:, 0]
+            clip_len = trim_bounds[:, 1] - trim_bounds[:, 0]
+            if (clip_len < 1).any():
+                raise ValueError('clip {} is empty after silence trimming'.format(int(np.argmax(clip_len < 1))))
     key = (dev.index, n_fft, win_length, hop_length, cfg.precision, cfg.sampling_rate, cfg.n_mels,
-           cfg.mel_fmin, cfg.mel_fmax, int(reduction), sample_off.tobytes())
+           cfg.mel_fmin, cfg.mel_fmax, int(reduction), clip_start.tobytes(), clip_len.tobytes())
 
     def factory():
         h = ctypes.c_void_p()
         with torch.cuda.device(dev):
-            _lib.check(lib.sstts_feat_plan_create(ctypes.byref(cfg), n,
-                                                  sample_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                                  int(reduction), ctypes.byref(h)))
+            _lib.check(lib.sstts_feat_plan_create_ranges(ctypes.byref(cfg), n, clip_start.ctypes.data_as(i64p),
+                                                         clip_len.ctypes.data_as(i64p), int(reduction),
+                                                         ctypes.byref(h)))
         return _Plan(h, lib.sstts_feat_plan_destroy)
 
     plan = _feat_plans.get(key, factory)
@@ -271,16 +292,12 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     frame_off = np.ctypeslib.as_array(lib.sstts_feat_frame_offsets(plan.handle), shape=(n + 1,)).copy()
     row_off = np.ctypeslib.as_array(lib.sstts_feat_row_offsets(plan.handle), shape=(n + 1,)).copy()
     res = FeatureBatch(n, [int(frame_off[i + 1] - frame_off[i]) for i in range(n)], row_off, reduction)
+    res.trim_bounds = trim_bounds
     if need_mel and cfg.n_mels > 0:
         res.mel_basis = np.ctypeslib.as_array(lib.sstts_feat_mel_basis(plan.handle),
                                               shape=(cfg.n_mels, n_bins)).copy()
 
     with torch.cuda.device(dev):
-        wav_host = torch.empty(int(sample_off[-1]), dtype=torch.float32, pin_memory=True)
-        dst = wav_host.numpy()
-        for i, w in enumerate(wavs):
-            np.copyto(dst[sample_off[i]:sample_off[i + 1]], w, casting='unsafe')
-        wav_dev = wav_host.to(dev, non_blocking=True)
         out = _lib.FeatOutputs()
         spec_dev = torch.empty((rows, n_bins, 2), dtype=torch.float32, device=dev) if want_spec else None
         lin_dev = torch.empty((rows, n_bins), dtype=torch.float32, device=dev) if want_lin else None
@@ -302,18 +319,10 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             res.lin_db, res.mel_db, res.mel_raw, res.minmax = lin_dev, mel_dev, raw_dev, mm_dev
             return res
 
-        def to_host(t):
-            if t is None:
-                return None
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            return h
-
-        spec_h, lin_h, mel_h, raw_h, mm_h = [to_host(t) for t in (spec_dev, lin_dev, mel_dev, raw_dev, mm_dev)]
+        res.spec = _hostio.download(spec_dev).view(np.complex64).reshape(rows, n_bins) if want_spec else None
+        res.lin_db = _hostio.download(lin_dev) if want_lin else None
+        res.mel_db = _hostio.download(mel_dev) if want_mel else None
+        res.mel_raw = _hostio.download(raw_dev) if want_mel_raw else None
+        res.minmax = _hostio.download(mm_dev) if want_minmax else None
         torch.cuda.current_stream().synchronize()
-    res.spec = torch.view_as_complex(spec_h).numpy() if spec_h is not None else None
-    res.lin_db = lin_h.numpy() if lin_h is not None else None
-    res.mel_db = mel_h.numpy() if mel_h is not None else None
-    res.mel_raw = raw_h.numpy() if raw_h is not None else None
-    res.minmax = mm_h.numpy() if mm_h is not None else None
     return res

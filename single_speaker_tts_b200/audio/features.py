@@ -32,17 +32,19 @@ def mel_scale_spectrogram(wav, n_fft, sampling_rate, n_mels, fmin, fmax, hop_len
 
 def features_batch(wavs, n_fft, hop_length, win_length, sampling_rate, n_mels, fmin, fmax,
                    linear_ref_db, linear_mag_max_db, mel_mag_ref_db, mel_mag_max_db, reduction=1,
-                   precision='f64'):
+                   precision='f64', trim=None):
     """Batched ``load_audio`` core (reference datasets/lj_speech.py:124-156 after decode/trim):
     one STFT per clip, fused |.| -> dB -> normalise for the linear and the mel spectrogram,
     reduction padding and folding.  Returns a list of ``(mel, lin)`` float32 pairs shaped
-    ``(ceil(T/r), r * n_mels)`` and ``(ceil(T/r), r * (1 + n_fft/2))``."""
+    ``(ceil(T/r), r * n_mels)`` and ``(ceil(T/r), r * (1 + n_fft/2))``.
+    ``trim=(top_db, frame_length, hop_length)`` runs the ``librosa.effects.trim`` step of
+    datasets/lj_speech.py:119 on the device first."""
     res = _runtime.stft_features_batch(list(wavs), n_fft, hop_length, win_length,
                                        sampling_rate=sampling_rate, n_mels=n_mels, fmin=fmin,
                                        fmax=fmax, reduction=reduction, want_lin=True, want_mel=True,
                                        normalize=(linear_ref_db, linear_mag_max_db, mel_mag_ref_db,
                                                   mel_mag_max_db),
-                                       precision=precision)
+                                       precision=precision, trim=trim)
     out = []
     n_bins = 1 + n_fft // 2
     for i in range(res.n_clips):

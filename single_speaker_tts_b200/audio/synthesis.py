@@ -56,3 +56,22 @@ def spectrograms_to_wavs(mags, win_length, hop_length, n_fft, n_iter, angles=Non
                                             angles=angles, seed=seed, precision=precision,
                                             return_mse=return_mse)
     return (wavs, mses) if return_mse else wavs
+
+
+def model_outputs_to_wavs(spectrograms, ref_db, max_db, magnitude_power, win_length, hop_length, n_fft,
+                          n_iter, seed=None, precision='f32'):
+    """Model output -> waveforms in one device call (extension; replaces
+    tacotron/inference.py:92-101 + :170-188 and tacotron/serve.py:39-72).
+
+    ``spectrograms``: iterable of normalised linear spectrograms exactly as ``session.run`` returns
+    them, ``(T, 1 + n_fft/2)`` float32 in [0, 1] (a ``(B, T, bins)`` array works too).  The
+    de-normalisation ``inv_normalize_decibel(spec.T, ref_db, max_db)`` -> ``decibel_to_magnitude``
+    -> ``** magnitude_power`` runs fused on the device (the reference passes the MEL constants
+    here, tacotron/inference.py:96-98), followed by ``n_iter`` Griffin-Lim iterations.  Raises the
+    reference's AssertionError if a de-normalised value falls below -100 dB.
+    """
+    specs = [np.asarray(s) for s in spectrograms]
+    wavs, _ = _runtime.griffin_lim_batch(specs, win_length, hop_length, n_fft, n_iter, seed=seed,
+                                         precision=precision,
+                                         denormalize=(ref_db, max_db, magnitude_power))
+    return wavs

@@ -12,8 +12,11 @@
 namespace sstts {
 
 // Frames per tile = warps per CTA: every tile is processed in one round, one frame per warp.
-constexpr int kTileFrames = 8;
-constexpr int kWarps = 8;
+#ifndef SSTTS_WARPS
+#define SSTTS_WARPS 8
+#endif
+constexpr int kTileFrames = SSTTS_WARPS;
+constexpr int kWarps = SSTTS_WARPS;
 
 // Smallest tile of a multi-tile utterance: (ft + 1) * hop >= win keeps same-parity spans and a
 // tile's two edge regions disjoint (>= 4 for win 1102 / hop 275).
@@ -84,26 +87,29 @@ inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int h
 
 struct FeatPlanHost {
   int n_clips = 0, win = 0, hop = 0, span_max = 0, reduction = 1;
-  std::vector<long long> sample_off, frame_off, row_off;
+  std::vector<long long> sample_off, sample_len, frame_off, row_off;   // sample_off: clip starts
   std::vector<FeatTile> tiles;
   long long total_frames = 0, total_rows = 0;
 };
 
-inline bool build_feat_plan(int n_clips, const long long* sample_off, int n_fft, int win, int hop,
-                            int reduction, FeatPlanHost& P, std::string& err) {
+// clip_start[c] / clip_len[c]: first sample and length of clip c inside the packed wav buffer
+// (clips need not be contiguous: trimmed clips keep their place in the untrimmed upload).
+inline bool build_feat_plan(int n_clips, const long long* clip_start, const long long* clip_len, int n_fft,
+                            int win, int hop, int reduction, FeatPlanHost& P, std::string& err) {
   if (n_fft != 2048 && n_fft != 1024 && n_fft != 512) { err = "n_fft must be 2048, 1024 or 512"; return false; }
   if (win < 2 || win > n_fft || hop < 1) { err = "need hop >= 1 and 2 <= win <= n_fft"; return false; }
   if ((n_fft - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
   if (reduction < 1) reduction = 1;
   P.n_clips = n_clips; P.win = win; P.hop = hop; P.reduction = reduction;
-  P.sample_off.assign(sample_off, sample_off + n_clips + 1);
+  P.sample_off.assign(clip_start, clip_start + n_clips);
+  P.sample_len.assign(clip_len, clip_len + n_clips);
   P.frame_off.assign(n_clips + 1, 0);
   P.row_off.assign(n_clips + 1, 0);
   P.tiles.clear();
   P.span_max = win;
   for (int c = 0; c < n_clips; ++c) {
-    const long long N = sample_off[c + 1] - sample_off[c];
-    if (N < 1 || N > (1LL << 30)) { err = "every clip needs between 1 and 2^30 samples"; return false; }
+    const long long N = clip_len[c];
+    if (clip_start[c] < 0 || N < 1 || N > (1LL << 30)) { err = "every clip needs between 1 and 2^30 samples"; return false; }
     const long long T = 1 + N / hop;
     const long long rows = ((T + reduction - 1) / reduction) * reduction;
     P.frame_off[c + 1] = P.frame_off[c] + T;

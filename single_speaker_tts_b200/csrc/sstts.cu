@@ -145,6 +145,7 @@ struct sstts_feat_plan {
   MelCSR mel;
   std::vector<double> mel_dense;
   long long* d_sample_off = nullptr;
+  long long* d_sample_len = nullptr;
   long long* d_frame_off = nullptr;
   long long* d_row_off = nullptr;
   FeatTile* d_tiles = nullptr;
@@ -298,6 +299,26 @@ __global__ void random_phase_kernel(unsigned long long seed, long long n, float2
   }
 }
 
+// tacotron/inference.py:94-101,175: normalised model output -> dB (inv_normalize_decibel) ->
+// magnitude (decibel_to_magnitude) -> magnitude ** power, in float32 like the reference.
+// mag ** power = 10 ** (dB * power / 20).  *flag is set when a dB value is below -100
+// (the reference raises AssertionError, audio/conversion.py:47-49).
+__global__ void denormalize_magnitude_kernel(const float* __restrict__ x, long long n, float ref_db,
+                                             float range_db, float power, float* __restrict__ out,
+                                             int* flag) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float c = power * 0.16609640474436813f;   // log2(10) / 20
+  bool bad = false;
+  for (; i < n; i += stride) {
+    const float v = fminf(fmaxf(x[i], 0.0f), 1.0f);
+    const float db = (v - 1.0f) * range_db + ref_db;
+    bad |= db < -100.0f;
+    out[i] = exp2f(db * c);
+  }
+  if (bad && flag) atomicOr(flag, 1);
+}
+
 __global__ void minmax_init_kernel(long long* mm, int n_clips) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_clips * 4) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
@@ -317,7 +338,8 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   const FeatPlanHost& H = P->host;
   FeatArgs<T> A;
   A.wav = wav;
-  A.sample_off = P->d_sample_off; A.frame_off = P->d_frame_off; A.row_off = P->d_row_off;
+  A.sample_off = P->d_sample_off; A.sample_len = P->d_sample_len;
+  A.frame_off = P->d_frame_off; A.row_off = P->d_row_off;
   A.tiles = P->d_tiles; A.n_tiles = (int)H.tiles.size();
   A.tab = tables_view<T>(P->tab);
   A.mel_ptr = P->d_mel_ptr; A.mel_k0 = P->d_mel_k0; A.mel_w = reinterpret_cast<const T*>(P->d_mel_w);
@@ -396,20 +418,33 @@ int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream)
   return 0;
 }
 
+int sstts_denormalize_magnitude(const float* norm_dev, int64_t n, double ref_db, double max_db,
+                                double power, float* mag_out_dev, int* flag_dev, void* stream) {
+  if (n < 0 || (n > 0 && (!norm_dev || !mag_out_dev))) return fail(SSTTS_ERR_INVALID, "bad denormalize arguments");
+  if (n == 0) return 0;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  denormalize_magnitude_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      norm_dev, n, (float)ref_db, (float)(fabs(ref_db) + fabs(max_db)), (float)power, mag_out_dev, flag_dev);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ features
-int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int64_t* sample_off_host,
-                           int reduction, sstts_feat_plan** plan_out) {
+int sstts_feat_plan_create_ranges(const sstts_stft_config* cfg, int n_clips, const int64_t* clip_start_host,
+                                  const int64_t* clip_len_host, int reduction, sstts_feat_plan** plan_out) {
   if (plan_out) *plan_out = nullptr;
   int rc = check_config(cfg, true);
   if (rc) return rc;
-  if (!plan_out || !sample_off_host || n_clips < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
+  if (!plan_out || !clip_start_host || !clip_len_host || n_clips < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
   if (cfg->n_mels < 0 || cfg->n_mels > 1024) return fail(SSTTS_ERR_INVALID, "n_mels out of range");
   sstts_feat_plan* P = new (std::nothrow) sstts_feat_plan();
   if (!P) return fail(SSTTS_ERR_INVALID, "out of host memory");
   P->cfg = *cfg;
   std::string err;
-  std::vector<long long> so(sample_off_host, sample_off_host + n_clips + 1);
-  if (!build_feat_plan(n_clips, so.data(), cfg->n_fft, cfg->win_length, cfg->hop_length, reduction, P->host, err)) {
+  std::vector<long long> cs(clip_start_host, clip_start_host + n_clips), cl(clip_len_host, clip_len_host + n_clips);
+  if (!build_feat_plan(n_clips, cs.data(), cl.data(), cfg->n_fft, cfg->win_length, cfg->hop_length, reduction,
+                       P->host, err)) {
     delete P;
     return fail(SSTTS_ERR_INVALID, err);
   }
@@ -430,6 +465,7 @@ int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int6
     }
   }
   if (!rc) rc = upload(P->host.sample_off, &P->d_sample_off);
+  if (!rc) rc = upload(P->host.sample_len, &P->d_sample_len);
   if (!rc) rc = upload(P->host.frame_off, &P->d_frame_off);
   if (!rc) rc = upload(P->host.row_off, &P->d_row_off);
   if (!rc) rc = upload(P->host.tiles, &P->d_tiles);
@@ -438,10 +474,34 @@ int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int6
   return 0;
 }
 
+int sstts_feat_plan_create(const sstts_stft_config* cfg, int n_clips, const int64_t* sample_off_host,
+                           int reduction, sstts_feat_plan** plan_out) {
+  if (plan_out) *plan_out = nullptr;
+  if (!sample_off_host || n_clips < 1) return fail(SSTTS_ERR_INVALID, "bad plan arguments");
+  std::vector<int64_t> cs(n_clips), cl(n_clips);
+  for (int c = 0; c < n_clips; ++c) { cs[c] = sample_off_host[c]; cl[c] = sample_off_host[c + 1] - sample_off_host[c]; }
+  return sstts_feat_plan_create_ranges(cfg, n_clips, cs.data(), cl.data(), reduction, plan_out);
+}
+
+int sstts_trim_bounds(const float* wav_dev, int n_clips, const int64_t* clip_start_dev,
+                      const int64_t* clip_len_dev, double top_db, int frame_length, int hop_length,
+                      int64_t* bounds_dev, void* stream) {
+  if (!wav_dev || !clip_start_dev || !clip_len_dev || !bounds_dev || n_clips < 1 || frame_length < 2 ||
+      hop_length < 1)
+    return fail(SSTTS_ERR_INVALID, "bad trim arguments");
+  int grid = n_clips < 148 * 8 ? n_clips : 148 * 8;
+  trim_bounds_kernel<256><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      wav_dev, reinterpret_cast<const long long*>(clip_start_dev), reinterpret_cast<const long long*>(clip_len_dev),
+      n_clips, frame_length, hop_length, top_db, reinterpret_cast<long long*>(bounds_dev));
+  CU(cudaGetLastError());
+  return 0;
+}
+
 void sstts_feat_plan_destroy(sstts_feat_plan* P) {
   if (!P) return;
   P->tab.release();
-  cudaFree(P->d_sample_off); cudaFree(P->d_frame_off); cudaFree(P->d_row_off); cudaFree(P->d_tiles);
+  cudaFree(P->d_sample_off); cudaFree(P->d_sample_len); cudaFree(P->d_frame_off); cudaFree(P->d_row_off);
+  cudaFree(P->d_tiles);
   cudaFree(P->d_mel_ptr); cudaFree(P->d_mel_k0); cudaFree(P->d_mel_w);
   delete P;
 }

@@ -503,7 +503,8 @@ struct FeatTile { int clip, a, b, last; };  // frames [a, b) of clip; last = til
 
 template <typename T> struct FeatArgs {
   const float* wav;               // packed clips
-  const long long* sample_off;    // [n_clips + 1]
+  const long long* sample_off;    // [n_clips] first sample of every clip in `wav`
+  const long long* sample_len;    // [n_clips] clip lengths N_c
   const long long* frame_off;     // [n_clips + 1] (frame counts T = 1 + N / hop)
   const long long* row_off;       // [n_clips + 1] output row offsets (>= frames: zero pad rows)
   const FeatTile* tiles;
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   auto issue_stage = [&](int t, float* buf) {
     const FeatTile tl = A.tiles[t];
     const long long soff = A.sample_off[tl.clip];
-    const int n_samples = (int)(A.sample_off[tl.clip + 1] - soff);
+    const int n_samples = (int)A.sample_len[tl.clip];
     const int span_lo = tl.a * hop + lpad;
     const int span = (tl.b - tl.a - 1) * hop + win;
     const float* x = A.wav + soff;
@@ -750,6 +751,77 @@ SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_
          sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win)) +
          sizeof(float) * 2 * (size_t)round_up4(span_max) + sizeof(T) * (size_t)round_up4(mel_nnz) +
          sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
+}
+
+// =============================================================================================
+// Silence trimming -- librosa.effects.trim(y, top_db, ref=np.max, frame_length, hop_length) as
+// called by datasets/lj_speech.py:119 (defaults 60 / 2048 / 512): frame mean-square energy over the
+// centre-reflect-padded clip, frames within top_db of the loudest are "non-silent", the clip is cut
+// to [first * hop, min(N, (last + 1) * hop)).  One CTA per clip; sums in float64.
+// =============================================================================================
+constexpr int TRIM_CACHE_FRAMES = 2048;   // per-frame energies kept in shared memory (recomputed beyond)
+
+template <int NT>
+__global__ void __launch_bounds__(NT) trim_bounds_kernel(const float* __restrict__ wav,
+                                                         const long long* __restrict__ clip_start,
+                                                         const long long* __restrict__ clip_len, int n_clips,
+                                                         int frame_length, int hop_length, double top_db,
+                                                         long long* __restrict__ bounds) {
+  __shared__ double s_ms[TRIM_CACHE_FRAMES];
+  __shared__ double s_red[NT / 32];
+  __shared__ int s_first, s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  for (int clip = blockIdx.x; clip < n_clips; clip += gridDim.x) {
+    const float* x = wav + clip_start[clip];
+    const int N = (int)clip_len[clip];
+    const int n_frames = 1 + N / hop_length;
+    const int half = frame_length / 2;
+    auto frame_ms = [&](int f) -> double {   // warp-collective: mean square of frame f
+      double acc = 0.0;
+      const int base = f * hop_length - half;
+      for (int i = lane; i < frame_length; i += 32) {
+        int q = base + i;
+        if (q < 0 || q >= N) q = reflect_index(q, N);
+        const double v = (double)x[q];
+        acc += v * v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      return acc / (double)frame_length;
+    };
+    // pass 1: energies (cached) and their maximum
+    double mx = 0.0;
+    for (int f = warp; f < n_frames; f += NW) {
+      const double ms = frame_ms(f);
+      if (lane == 0 && f < TRIM_CACHE_FRAMES) s_ms[f] = ms;
+      mx = fmax(mx, ms);
+    }
+    if (lane == 0) s_red[warp] = mx;
+    if (tid == 0) { s_first = 0x7fffffff; s_last = -1; }
+    __syncthreads();
+    mx = 0.0;
+    for (int w = 0; w < NW; ++w) mx = fmax(mx, s_red[w]);
+    // power_to_db(mse, ref=np.max, amin=1e-10, top_db=None) > -top_db
+    const double ref_db = 10.0 * log10(fmax(1e-10, mx));
+    for (int f = warp; f < n_frames; f += NW) {
+      const double ms = f < TRIM_CACHE_FRAMES ? s_ms[f] : frame_ms(f);
+      const bool loud = 10.0 * log10(fmax(1e-10, ms)) - ref_db > -top_db;
+      if (lane == 0 && loud) { atomicMin(&s_first, f); atomicMax(&s_last, f); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      long long start = 0, end = 0;
+      if (s_last >= 0) {
+        start = (long long)s_first * hop_length;
+        end = (long long)(s_last + 1) * hop_length;
+        if (end > N) end = N;
+      }
+      bounds[2 * clip] = start;
+      bounds[2 * clip + 1] = end;
+    }
+    __syncthreads();
+  }
 }
 
 }  // namespace sstts

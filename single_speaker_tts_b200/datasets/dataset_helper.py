@@ -9,7 +9,6 @@ import os
 import numpy as np
 
 from ..audio.conversion import ms_to_samples
-from ..audio.effects import trim
 from ..audio.features import features_batch
 from ..audio.io import load_wav
 from ..params import model_params
@@ -42,12 +41,13 @@ class DatasetHelper:
         sr = sampling_rate or model_params.sampling_rate
         win_len = ms_to_samples(model_params.win_len, model_params.sampling_rate)
         hop_len = ms_to_samples(model_params.win_hop, model_params.sampling_rate)
-        if trim_silence:
-            wavs = [trim(w)[0] for w in wavs]
+        # librosa.effects.trim defaults (datasets/lj_speech.py:119): top_db 60, frames 2048 / 512;
+        # runs as a device kernel on the same upload the feature kernel reads
         return features_batch(wavs, model_params.n_fft, hop_len, win_len, sr, model_params.n_mels,
                               model_params.mel_fmin, model_params.mel_fmax, cls.linear_ref_db,
                               cls.linear_mag_max_db, cls.mel_mag_ref_db, cls.mel_mag_max_db,
-                              reduction=model_params.reduction, precision=precision)
+                              reduction=model_params.reduction, precision=precision,
+                              trim=(60.0, 2048, 512) if trim_silence else None)
 
     @classmethod
     def load_audio(cls, file_path):

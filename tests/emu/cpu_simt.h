@@ -31,6 +31,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
+#define __shared__ static   /* blocks run one at a time, so function-static == block-shared */
 #define SSTTS_HD inline
 #define SSTTS_D inline
 

@@ -28,6 +28,7 @@ def load():
                                           [ctypes.c_int, _lp, ctypes.c_int, _fp, _fp, _fp, _fp, _dp,
                                            _dp, ctypes.c_int] + [ctypes.c_double] * 5 + [ctypes.c_int])
         lib.emu_mel_basis.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double] * 2 + [_dp]
+        lib.emu_trim_bounds.argtypes = [_fp, ctypes.c_int, _lp, _lp, ctypes.c_double, ctypes.c_int, ctypes.c_int, _lp]
         _lib = lib
     return sys.modules[__name__]
 
@@ -86,3 +87,13 @@ def mel_basis(sr, n_fft, n_mels, fmin, fmax):
     mb = np.zeros((n_mels, n_fft // 2 + 1))
     _lib.emu_mel_basis(sr, n_fft, n_mels, float(fmin), float(fmax), mb.ctypes.data_as(_dp))
     return mb
+
+
+def trim_bounds(wavs, top_db=60.0, frame_length=2048, hop_length=512):
+    lens = np.asarray([len(w) for w in wavs], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    wav = np.concatenate(wavs).astype(np.float32)
+    bounds = np.zeros((len(wavs), 2), dtype=np.int64)
+    _lib.emu_trim_bounds(wav.ctypes.data_as(_fp), len(wavs), starts.ctypes.data_as(_lp), lens.ctypes.data_as(_lp),
+                         float(top_db), frame_length, hop_length, bounds.ctypes.data_as(_lp))
+    return bounds

@@ -107,7 +107,9 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
                  double lin_max, double mel_ref, double mel_max, double power, int grid_cap) {
   FeatPlanHost H;
   std::string err;
-  if (!build_feat_plan(n_clips, sample_off, n_fft, win, hop, reduction, H, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
+  std::vector<long long> cs(n_clips), cl(n_clips);
+  for (int c = 0; c < n_clips; ++c) { cs[c] = sample_off[c]; cl[c] = sample_off[c + 1] - sample_off[c]; }
+  if (!build_feat_plan(n_clips, cs.data(), cl.data(), n_fft, win, hop, reduction, H, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
   HostTables<T> tabs;
   fill_tables<T>(win, tabs);
   MelCSR M;
@@ -118,7 +120,7 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   }
   std::vector<long long> mm(4 * (size_t)n_clips);
   FeatArgs<T> A;
-  A.wav = wav; A.sample_off = H.sample_off.data(); A.frame_off = H.frame_off.data();
+  A.wav = wav; A.sample_off = H.sample_off.data(); A.sample_len = H.sample_len.data(); A.frame_off = H.frame_off.data();
   A.row_off = H.row_off.data(); A.tiles = H.tiles.data(); A.n_tiles = (int)H.tiles.size();
   A.tab = tabs.view();
   A.mel_ptr = M.ptr.data(); A.mel_k0 = M.k0.data(); A.mel_w = mw.data(); A.n_mels = n_mels; A.mel_nnz = (int)mw.size();
@@ -188,6 +190,14 @@ int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels,
   if (stats) return emu_feat_run<float, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
   return emu_feat_run<float, DynGeom, kWarps>(FEAT_ARGS);
 #undef FEAT_ARGS
+}
+
+int emu_trim_bounds(const float* wav, int n_clips, const long long* clip_start, const long long* clip_len,
+                    double top_db, int frame_length, int hop_length, long long* bounds) {
+  emu::launch(dim3(n_clips < 3 ? n_clips : 3), dim3(256), 0, [&]() {
+    trim_bounds_kernel<256>(wav, clip_start, clip_len, n_clips, frame_length, hop_length, top_db, bounds);
+  });
+  return 0;
 }
 
 int emu_mel_basis(int sr, int n_fft, int n_mels, double fmin, double fmax, double* dense_out) {

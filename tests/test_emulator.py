@@ -122,3 +122,15 @@ def test_mel_basis_matches_oracle(emu):
         mb = emu.mel_basis(22050, n_fft, 80, 0, fmax)
         ref = lc.mel_filterbank(22050, n_fft, 80, 0, fmax)
         assert np.abs(mb - ref).max() < 1e-15 and ((mb != 0) == (ref != 0)).all()
+
+
+def test_trim_bounds_match_librosa_trim(emu):
+    """librosa.effects.trim (datasets/lj_speech.py:119) as a device kernel: same (start, end)."""
+    rng = np.random.default_rng(3)
+    sp = speech_like_clip(12000, rng)
+    wavs = [np.concatenate([np.zeros(4000, np.float32), sp, np.zeros(5000, np.float32)]),
+            sp[:3000].copy(), np.zeros(6000, np.float32),
+            np.concatenate([1e-5 * rng.normal(size=3000).astype(np.float32), sp[:7000], 1e-6 * np.ones(2500, np.float32)])]
+    got = emu.trim_bounds(wavs)
+    for w, b in zip(wavs, got):
+        assert tuple(b) == tuple(lc.trim(w)[1])

@@ -227,3 +227,30 @@ def test_full_size_round_trip_properties():
         for c, w in zip(sub, wavs):
             assert w.shape == (HOP * (len(c) // HOP),)
             assert rel_l2(w, c[:len(w)]) < 2e-5
+
+
+def test_model_output_glue_matches_inference_recipe(golden_dir):
+    """tacotron/inference.py:94-101,175 fused on the device == the oracle recipe + Griffin-Lim."""
+    g = np.load(golden_dir + '/gl_fixture.npz')
+    out = g['model_output']                                   # (T, 1025) normalised, as session.run returns
+    mag = ra.inference_postprocess(out)
+    np.random.seed(11)
+    ref = synthesis.spectrograms_to_wavs([mag, mag[:, :50]], WIN, HOP, NFFT, 8, seed=99)
+    got = synthesis.model_outputs_to_wavs([out, out[:50]], 6.02, 99.89, 1.3, WIN, HOP, NFFT, 8, seed=99)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and rel_l2(a, b) < 1e-4
+    with pytest.raises(AssertionError, match='smaller -100 dB'):
+        synthesis.model_outputs_to_wavs([np.zeros((20, 1025), np.float32)], 6.02, 120.0, 1.3, WIN, HOP, NFFT, 1)
+
+
+def test_trim_batch_matches_oracle():
+    from single_speaker_tts_b200.audio import effects
+    rng = np.random.default_rng(3)
+    sp = speech_like_clip(30000, rng)
+    wavs = [np.concatenate([np.zeros(4000, np.float32), sp, np.zeros(5000, np.float32)]), sp[:3000].copy(),
+            np.concatenate([1e-5 * rng.normal(size=3000).astype(np.float32), sp[:7000], 1e-6 * np.ones(2500, np.float32)])]
+    trimmed, bounds = effects.trim_batch(wavs)
+    for w, t, b in zip(wavs, trimmed, bounds):
+        yr, br = lc.trim(w)
+        assert tuple(b) == tuple(br) and np.array_equal(t, yr)
+        assert tuple(effects.trim(w)[1]) == tuple(br)
