@@ -7,12 +7,13 @@
 //     twiddle W_1024^(l * k1)   (table in shared memory, conflict-free [k1][l] layout)
 //     32 x 32 transpose through a padded per-warp shared-memory plane (the only exchange)
 //     pass 2  32-point FFT over the register index again
-// Input and output use the same "element = 32 * slot + lane" indexing.  Two flavours:
-//     DIF (analysis):   natural slot order in, bit-reversed slot order out
-//     DIT (synthesis):  bit-reversed slot order in, natural slot order out
-// so a forward DIF transform can hand its registers straight to an inverse DIT transform
-// (the Griffin-Lim iteration does exactly that) and no register permutation is ever
-// executed: every slot index is a compile-time constant after unrolling.
+// Input and output use the same "element = 32 * slot + lane" indexing.  A 32-point pass is
+// either DIF (natural slot order in, bit-reversed out) or DIT (bit-reversed in, natural out).
+// Slot order is free wherever data comes from or goes to memory, so the kernels use DIT
+// (FMA-fused butterflies, zero-padding pruned for free) for three of the four passes of a
+// Griffin-Lim iteration and DIF only for the first inverse pass, which takes the forward
+// result in natural order straight from the registers: no register permutation is ever
+// executed, every slot index is a compile-time constant after unrolling.
 // No 1/N scaling is applied here -- callers fold it into the synthesis window.
 //
 // The 32-point register FFT is radix-2 with the trivial twiddles (1, -i, (1-i)/sqrt2, ...)
@@ -88,7 +89,34 @@ SSTTS_HD void dif_stage(T (&re)[32], T (&im)[32]) {
   }
 }
 
-// One decimation-in-time stage: (a, b) -> (a + b W, a - b W).
+// FMA-fused decimation-in-time butterfly (a, b) -> (a + b W, a - b W): the sum is built with
+// chained FMAs and the difference as 2 a - (a + b W), i.e. 6 instructions for a general twiddle
+// instead of 8 (complex multiply + two complex adds).
+template <typename T, bool INV>
+SSTTS_HD void dit_butterfly(T& ar, T& ai, T& br, T& bi, int idx) {
+  T sr, si;   // a + b W
+  if (idx == 0) {
+    sr = ar + br; si = ai + bi;
+    br = ar - br; bi = ai - bi;
+    ar = sr; ai = si;
+    return;
+  }
+  if (idx == 8) {   // W = -/+ i
+    if (!INV) { sr = ar + bi; si = ai - br; const T dr = ar - bi, di = ai + br; br = dr; bi = di; }
+    else      { sr = ar - bi; si = ai + br; const T dr = ar + bi, di = ai - br; br = dr; bi = di; }
+    ar = sr; ai = si;
+    return;
+  }
+  const T c = cos32<T>(idx), s = INV ? -sin32<T>(idx) : sin32<T>(idx);
+  // b W = (br c + bi s, bi c - br s) with W = c - i s
+  sr = fma(br, c, fma(bi, s, ar));
+  si = fma(bi, c, fma(-br, s, ai));
+  br = fma(T(2), ar, -sr);
+  bi = fma(T(2), ai, -si);
+  ar = sr; ai = si;
+}
+
+// One decimation-in-time stage over all 16 butterflies of span LEN.
 template <typename T, bool INV, int LEN>
 SSTTS_HD void dit_stage(T (&re)[32], T (&im)[32]) {
   constexpr int HALF = LEN / 2;
@@ -96,22 +124,36 @@ SSTTS_HD void dit_stage(T (&re)[32], T (&im)[32]) {
 #pragma unroll
   for (int g = 0; g < 32; g += LEN) {
 #pragma unroll
-    for (int j = 0; j < HALF; ++j) {
-      const int i0 = g + j, i1 = g + j + HALF;
-      T tr, ti;
-      mul_w32<T, INV>(re[i1], im[i1], j * TSTEP, tr, ti);
-      const T ar = re[i0], ai = im[i0];
-      re[i0] = ar + tr;
-      im[i0] = ai + ti;
-      re[i1] = ar - tr;
-      im[i1] = ai - ti;
+    for (int j = 0; j < HALF; ++j) dit_butterfly<T, INV>(re[g + j], im[g + j], re[g + j + HALF], im[g + j + HALF], j * TSTEP);
+  }
+}
+
+// First DIT stage (span 2, W = 1) when the input elements outside [ZLO, ZHI] are known to be zero
+// (zero-padded window): slot 2g holds element e = brev5(2g) < 16 and slot 2g + 1 element e + 16,
+// so most butterflies degenerate to copies / negations and cost nothing.
+template <typename T, int ZLO, int ZHI>
+SSTTS_HD void dit_stage2_pruned(T (&re)[32], T (&im)[32]) {
+#pragma unroll
+  for (int g = 0; g < 32; g += 2) {
+    const int e = brev5(g);
+    const bool a_zero = e < ZLO || e > ZHI, b_zero = e + 16 < ZLO || e + 16 > ZHI;
+    if (a_zero && b_zero) {
+      re[g] = T(0); im[g] = T(0); re[g + 1] = T(0); im[g + 1] = T(0);
+    } else if (a_zero) {
+      re[g] = re[g + 1]; im[g] = im[g + 1]; re[g + 1] = -re[g + 1]; im[g + 1] = -im[g + 1];
+    } else if (b_zero) {
+      re[g + 1] = re[g]; im[g + 1] = im[g];
+    } else {
+      const T ar = re[g], ai = im[g], br = re[g + 1], bi = im[g + 1];
+      re[g] = ar + br; im[g] = ai + bi; re[g + 1] = ar - br; im[g + 1] = ai - bi;
     }
   }
 }
 
 // In-register 32-point FFT.  DIT = false: element k in slot k -> result k in slot brev5(k).
-//                            DIT = true : element k in slot brev5(k) -> result k in slot k.
-template <typename T, bool INV, bool DIT>
+//                            DIT = true : element k in slot brev5(k) -> result k in slot k;
+//                            input elements outside [ZLO, ZHI] must be zero (default: none are).
+template <typename T, bool INV, bool DIT, int ZLO = 0, int ZHI = 31>
 SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
   if (!DIT) {
     dif_stage<T, INV, 32>(re, im);
@@ -120,7 +162,8 @@ SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
     dif_stage<T, INV, 4>(re, im);
     dif_stage<T, INV, 2>(re, im);
   } else {
-    dit_stage<T, INV, 2>(re, im);
+    if (ZLO > 0 || ZHI < 31) dit_stage2_pruned<T, ZLO, ZHI>(re, im);
+    else dit_stage<T, INV, 2>(re, im);
     dit_stage<T, INV, 4>(re, im);
     dit_stage<T, INV, 8>(re, im);
     dit_stage<T, INV, 16>(re, im);
@@ -136,34 +179,39 @@ constexpr int XPITCH = 33;
 constexpr int XPLANE_ELEMS = 32 * XPITCH;
 
 // 1024-point complex FFT across one warp; element index = 32 * slot + lane on both sides.
-//   DIT = false: slots natural in, bit-reversed out.   DIT = true: bit-reversed in, natural out.
+// Each 32-point pass is either DIF (natural slots in, bit-reversed out) or DIT (bit-reversed in,
+// natural out); P1_DIT / P2_DIT select them.  The slot order between the passes is free because
+// the data goes through the shared-memory transpose, so the only constraint is on the caller's
+// side: pass-1 input in (P1_DIT ? bit-reversed : natural) slots, result in
+// (P2_DIT ? natural : bit-reversed) slots.  DIT passes use the FMA-fused butterfly.
+// With P1_DIT, input elements (slots before bit reversal) outside [ZLO, ZHI] must be zero.
 // tw[a * 32 + b] = exp(-2 pi i a b / 1024); xp is this warp's private XPLANE_ELEMS plane.
-template <typename T, bool INV, bool DIT>
+template <typename T, bool INV, bool P1_DIT, bool P2_DIT, int ZLO = 0, int ZHI = 31>
 SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], T* xp, const typename cx_of<T>::type* tw,
                           int lane) {
   typedef typename cx_of<T>::type C;
-  fft32<T, INV, DIT>(re, im);
+  fft32<T, INV, P1_DIT, (P1_DIT ? ZLO : 0), (P1_DIT ? ZHI : 31)>(re, im);
 #pragma unroll
   for (int k1 = 1; k1 < 32; ++k1) {
-    const int p = DIT ? k1 : brev5(k1);  // slot holding pass-1 result k1
+    const int p = P1_DIT ? k1 : brev5(k1);  // slot holding pass-1 result k1
     const C w = tw[k1 * 32 + lane];
     const T vr = re[p], vi = im[p];
     if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
     else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
   }
 #pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = re[DIT ? k1 : brev5(k1)];
+  for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = re[P1_DIT ? k1 : brev5(k1)];
   __syncwarp();
 #pragma unroll
-  for (int n2 = 0; n2 < 32; ++n2) re[DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
+  for (int n2 = 0; n2 < 32; ++n2) re[P2_DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
   __syncwarp();
 #pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = im[DIT ? k1 : brev5(k1)];
+  for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = im[P1_DIT ? k1 : brev5(k1)];
   __syncwarp();
 #pragma unroll
-  for (int n2 = 0; n2 < 32; ++n2) im[DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
+  for (int n2 = 0; n2 < 32; ++n2) im[P2_DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
   __syncwarp();
-  fft32<T, INV, DIT>(re, im);
+  fft32<T, INV, P2_DIT>(re, im);
 }
 
 }  // namespace sstts

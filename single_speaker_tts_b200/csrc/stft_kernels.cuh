@@ -50,6 +50,9 @@ template <int WIN, int HOP, int NFFT_EFF = 2048> struct StaticGeom {
   SSTTS_HD constexpr int lpad() const { return (NFFT_EFF - WIN) / 2; }   // window offset in the frame
   SSTTS_HD constexpr int cpad() const { return NFFT_EFF / 2; }           // centre (reflect) padding
   SSTTS_HD constexpr int bin_shift() const { return NFFT_EFF == 2048 ? 0 : NFFT_EFF == 1024 ? 1 : 2; }
+  // packed elements z[n] (64 samples per register slot) that overlap the window; the rest are zero
+  static constexpr int ZLO = ((NFFT_EFF - WIN) / 2) / 64;
+  static constexpr int ZHI = ((NFFT_EFF - WIN) / 2 + WIN - 1) / 64;
 };
 struct DynGeom {
   int win_, hop_, nfft_;
@@ -60,6 +63,8 @@ struct DynGeom {
   SSTTS_HD int lpad() const { return (nfft_ - win_) / 2; }
   SSTTS_HD int cpad() const { return nfft_ / 2; }
   SSTTS_HD int bin_shift() const { return nfft_ == 2048 ? 0 : nfft_ == 1024 ? 1 : 2; }
+  static constexpr int ZLO = 0;
+  static constexpr int ZHI = 31;
 };
 
 // numpy.pad(mode='reflect') index map for any q (multi-bounce for short signals).
@@ -148,7 +153,7 @@ template <typename T> struct GLArgs {
 };
 
 template <typename T> SSTTS_D T fast_rsqrt(T x);
-template <> SSTTS_D float fast_rsqrt<float>(float x) { return rsqrtf(x); }
+template <> SSTTS_D float fast_rsqrt<float>(float x) { return sstts_rsqrt_approx(x); }
 template <> SSTTS_D double fast_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
 
 // Unit phasor of (xr, xi) times s;  (1, 0) * s when the bin is exactly zero
@@ -156,7 +161,9 @@ template <> SSTTS_D double fast_rsqrt<double>(double x) { return 1.0 / sqrt(x); 
 template <typename T>
 SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
   m2 = fma(xr, xr, xi * xi);   // explicit contraction: identical bits in every instantiation
-  const bool nz = m2 > T(0);
+  // |x|^2 below 1e-30 (|x| < 1e-15, far under the float32 FFT noise floor) counts as zero, which
+  // lets the float path use the single-instruction flush-to-zero MUFU.RSQ
+  const bool nz = m2 > T(1e-30);
   const T inv = nz ? fast_rsqrt<T>(m2) * s : T(0);
   yr = nz ? xr * inv : s;
   yi = xi * inv;
@@ -181,8 +188,8 @@ SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane) {
 }
 
 // The per-frame core of one Griffin-Lim step, on the packed spectrum held by the warp.
-//   in  (FROM_PHASE = false): re/im = Z = FFT1024(z) in bit-reversed slots
-//   out: re/im = 2 Z' (packed spectrum of |S| * E/|E|) in bit-reversed slots
+//   in  (FROM_PHASE = false): re/im = Z = FFT1024(z), element 32 r + lane in slot r
+//   out: re/im = 2 Z' (packed spectrum of |S| * E/|E|), same slots
 // Conjugate-pair identities (N = 1024, w = exp(-2 pi i k / 2048), Zn = Z[N-k]):
 //   2 X[k]   = (Zk + conj Zn) + w * (-i)(Zk - conj Zn)
 //   2 X[N-k] = conj((Zk + conj Zn) - w * (-i)(Zk - conj Zn))
@@ -200,9 +207,9 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
   const int partner = (32 - lane) & 31;
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
-    const int sl_mine = brev5(k2);
-    const int sl_part = brev5(31 - k2);
-    const int sl_alt = brev5((32 - k2) & 31);
+    const int sl_mine = k2;
+    const int sl_part = 31 - k2;
+    const int sl_alt = (32 - k2) & 31;
     const int k = lane + 32 * k2;
     const int kn = HALF - k;
     const C w = s_w2k[k];
@@ -251,7 +258,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
   }
   // k = 512 (lane 0, slot 16): X = conj(Z), Z' = conj(Y).
   if (lane == 0) {
-    const int sl = brev5(16);
+    const int sl = 16;
     const T s = fabs((T)srow[HALF / 2]);
     T yr, yi;
     if (!FROM_PHASE) {
@@ -387,10 +394,10 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         for (int n1 = 0; n1 < 32; ++n1) {
           const int m = 64 * n1 + 2 * lane;
           const int i = m - lpad;
-          re[n1] = (i >= 0 && i < win) ? fin[m] * s_win[i] : T(0);
-          im[n1] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * s_win[i + 1] : T(0);
+          re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * s_win[i] : T(0);      // DIT pass: bit-reversed slots
+          im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * s_win[i + 1] : T(0);
         }
-        warp_fft1024<T, false, false>(re, im, plane, s_tw, lane);
+        warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
         sstts_cp_async_wait_all();
         __syncwarp();
       }
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
         if (lane == 0) A.mse_frame[row] = mse_acc;
       }
-      warp_fft1024<T, true, true>(re, im, plane, s_tw, lane);
+      warp_fft1024<T, true, false, true>(re, im, plane, s_tw, lane);
       // windowed output frame into the (now dead) plane; slot index = m - mlo, zero outside
       // the window so that the pair store needs no per-element guard
 #pragma unroll
@@ -411,8 +418,9 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         if (m >= mlo && m < lpad + win + 1) {
           const T v0 = (i >= 0 && i < win) ? re[n1] * s_win[i] : T(0);
           const T v1 = (i + 1 >= 0 && i + 1 < win) ? im[n1] * s_win[i + 1] : T(0);
-          plane[m - mlo] = v0;
-          plane[m - mlo + 1] = v1;
+          typename cx_of<T>::type vv;
+          vv.x = v0; vv.y = v1;
+          *reinterpret_cast<typename cx_of<T>::type*>(plane + (m - mlo)) = vv;   // m - mlo is even
         }
       }
     }
@@ -638,17 +646,17 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
       for (int n1 = 0; n1 < 32; ++n1) {
         const int m = 64 * n1 + 2 * lane;
         const int i = m - lpad;
-        re[n1] = (i >= 0 && i < win) ? (T)fin[m] * s_win[i] : T(0);
-        im[n1] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * s_win[i + 1] : T(0);
+        re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * s_win[i] : T(0);      // DIT pass: bit-reversed slots
+        im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * s_win[i + 1] : T(0);
       }
-      warp_fft1024<T, false, false>(re, im, plane, s_tw, lane);
+      warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
       float* s_mag = reinterpret_cast<float*>(plane);  // transpose plane is dead: |S| of this frame
       const int partner = (32 - lane) & 31;
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
-        const int sl_mine = brev5(k2);
-        const int sl_part = brev5(31 - k2);
-        const int sl_alt = brev5((32 - k2) & 31);
+        const int sl_mine = k2;
+        const int sl_part = 31 - k2;
+        const int sl_alt = (32 - k2) & 31;
         const int k = lane + 32 * k2;
         const int kn = HALF - k;
         const C w = s_w2k[k];
@@ -686,7 +694,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
         }
       }
       if (lane == 0) {   // k = 512: X = conj(Z)
-        const int sl = brev5(16);
+        const int sl = 16;
         const int kh = (HALF / 2) >> bshift;
         const float fr = (float)re[sl], fi = -(float)im[sl];
         if (A.spec_out) A.spec_out[row * n_bins + kh] = make_float2(fr, fi);

@@ -1,0 +1,53 @@
+// AddressSanitizer run of the emulated kernels (compute-sanitizer is unavailable on the GPU pool):
+//   g++ -O1 -g -std=c++20 -fsanitize=address -pthread -I. -I../../single_speaker_tts_b200/csrc \
+//       asan_main.cpp -o asan_main && ./asan_main
+// Every shared-memory carve-up and every global buffer is an exactly-sized heap block, so an
+// out-of-bounds access of a kernel aborts here.
+#include "emu_driver.cpp"
+
+int main() {
+  std::vector<long long> frames = {1, 2, 5, 9, 13, 30, 8, 16};
+  std::vector<long long> fo(1, 0);
+  for (long long t : frames) fo.push_back(fo.back() + t);
+  const long long T = fo.back();
+  std::vector<float> mag((size_t)T * 1025), phase((size_t)T * 1025 * 2);
+  unsigned s = 1;
+  for (auto& v : mag) { s = s * 1664525u + 1013904223u; v = (s >> 8) * (1.0f / 16777216.0f); }
+  for (size_t i = 0; i < phase.size(); i += 2) {
+    s = s * 1664525u + 1013904223u;
+    const float a = 6.2831853f * (s >> 8) * (1.0f / 16777216.0f);
+    phase[i] = cosf(a); phase[i + 1] = sinf(a);
+  }
+  long long n_out = 0;
+  for (long long t : frames) n_out += 275 * (t - 1);
+  std::vector<float> wav((size_t)n_out);
+  std::vector<double> mse((size_t)T);
+  for (int prec = 0; prec < 2; ++prec) {
+    if (emu_griffin_lim(1102, 275, prec, (int)frames.size(), fo.data(), mag.data(), phase.data(), 2, wav.data(),
+                        mse.data(), 3)) return 1;
+    if (emu_griffin_lim(1024, 256, prec, (int)frames.size(), fo.data(), mag.data(), phase.data(), 1, wav.data(),
+                        nullptr, 2)) return 1;
+  }
+  std::vector<long long> lens = {1, 2, 274, 275, 276, 1500, 5000, 9000};
+  std::vector<long long> so(1, 0);
+  for (long long n : lens) so.push_back(so.back() + n);
+  std::vector<float> x((size_t)so.back());
+  for (auto& v : x) { s = s * 1664525u + 1013904223u; v = (s >> 8) * (1.0f / 16777216.0f) - 0.5f; }
+  for (int prec = 0; prec < 2; ++prec) {
+    for (int cfgi = 0; cfgi < 2; ++cfgi) {
+      const int n_fft = cfgi ? 1024 : 2048, win = cfgi ? 1024 : 1102, hop = cfgi ? 256 : 275, r = cfgi ? 1 : 5;
+      const int nb = n_fft / 2 + 1;
+      long long rows = 0;
+      for (long long n : lens) { long long t = 1 + n / hop; rows += (t + r - 1) / r * r; }
+      std::vector<float> spec((size_t)rows * nb * 2), lin((size_t)rows * nb), mel((size_t)rows * 80);
+      std::vector<double> raw((size_t)rows * 80), mm(lens.size() * 4);
+      if (emu_stft_features(n_fft, win, hop, prec, 22050, 80, 0.0, cfgi ? 11025.0 : 8000.0, (int)lens.size(), so.data(), r,
+                            x.data(), spec.data(), lin.data(), mel.data(), raw.data(), mm.data(), 1, 35.66, 100.0, 6.02,
+                            99.89, 1.0, 3)) return 1;
+    }
+  }
+  std::vector<long long> cs(so.begin(), so.end() - 1), bounds(lens.size() * 2);
+  emu_trim_bounds(x.data(), (int)lens.size(), cs.data(), lens.data(), 60.0, 2048, 512, bounds.data());
+  printf("asan run ok\n");
+  return 0;
+}

@@ -144,6 +144,7 @@ static inline void sstts_cp_async16(void* smem_dst, const void* gmem_src) { std:
 static inline void sstts_cp_async4(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
 static inline void sstts_cp_async_wait_all() {}
 static inline float sstts_sqrt_approx(float x) { return sqrtf(x); }
+static inline float sstts_rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float sstts_log2_approx(float x) { return log2f(x); }
 static inline void sstts_cp_async_commit() {}
 static inline void sstts_cp_async_wait_group1() {}

@@ -45,16 +45,17 @@ void fft_test_kernel(const T* in, T* out, const typename cx_of<T>::type* tw) {
   T* xt = reinterpret_cast<T*>(smem);
   const int lane = threadIdx.x & 31;
   T re[32], im[32];
+  // forward: DIT/DIT (bit-reversed slots in, natural out); inverse: DIF/DIT (natural in and out)
+  constexpr bool P1_DIT = !INV;
   for (int r = 0; r < 32; ++r) {
-    const int slot = DIT ? brev5(r) : r;
+    const int slot = P1_DIT ? brev5(r) : r;
     re[slot] = in[2 * (32 * r + lane)];
     im[slot] = in[2 * (32 * r + lane) + 1];
   }
-  warp_fft1024<T, INV, DIT>(re, im, xt, tw, lane);
+  warp_fft1024<T, INV, P1_DIT, true>(re, im, xt, tw, lane);
   for (int r = 0; r < 32; ++r) {
-    const int slot = DIT ? r : brev5(r);
-    out[2 * (32 * r + lane)] = re[slot];
-    out[2 * (32 * r + lane) + 1] = im[slot];
+    out[2 * (32 * r + lane)] = re[r];
+    out[2 * (32 * r + lane) + 1] = im[r];
   }
 }
 
