@@ -102,6 +102,21 @@ SSTTS_D T window_sumsq(int p, int n_frames, int hop, int win, int lpad, const T*
   return acc;
 }
 
+// The window lives in shared memory with a zero guard on both sides and shifted by WIN_SHIFT(lpad)
+// elements, so that for every even frame position m the pair (w[m - lpad], w[m + 1 - lpad]) is
+// one aligned 8 / 16-byte load and reads zeros just outside the window.
+constexpr int WIN_TAB_PAD = 4;
+SSTTS_HD int win_shift(int lpad) { return (lpad & 1) ? 1 : 2; }
+template <typename T>
+SSTTS_D T* load_window_table(T* s_wtab, const T* g_window, int win, int lpad, int tid, int nthreads) {
+  T* s_win = s_wtab + win_shift(lpad);
+  for (int i = tid; i < round_up4(win + WIN_TAB_PAD); i += nthreads) {
+    const int j = i - win_shift(lpad);
+    s_wtab[i] = (j >= 0 && j < win) ? g_window[j] : T(0);
+  }
+  return s_win;
+}
+
 // np.finfo(np.float32).tiny -- librosa's guard for the window-sum division.
 #define SSTTS_F32_TINY 1.17549435e-38f
 
@@ -285,7 +300,7 @@ template <typename T> struct GLSmem {
     plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
     size_t o = sizeof(C) * 1024;
     off_w2k = o; o += sizeof(C) * 512;
-    off_win = o; o += sizeof(T) * round_up4(win);
+    off_win = o; o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_rw = o; o += sizeof(T) * round_up4(hop);
     off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
     off_mag = o; o += sizeof(float) * (size_t)warps * MAGROW;
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   const GLSmem<T> L(W, win, hop, A.span_max);
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = reinterpret_cast<C*>(smem + L.off_w2k);
-  T* s_win = reinterpret_cast<T*>(smem + L.off_win);
+  T* s_win = load_window_table<T>(reinterpret_cast<T*>(smem + L.off_win), A.tab.window, win, lpad, tid, W * 32);
   T* s_rw = reinterpret_cast<T*>(smem + L.off_rw);
   T* s_planes = reinterpret_cast<T*>(smem + L.off_plane);
   float* s_mag = reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
@@ -318,7 +333,6 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
 
   for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
-  for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
   __syncthreads();
   fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
   __syncthreads();
@@ -394,8 +408,11 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         for (int n1 = 0; n1 < 32; ++n1) {
           const int m = 64 * n1 + 2 * lane;
           const int i = m - lpad;
-          re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * s_win[i] : T(0);      // DIT pass: bit-reversed slots
-          im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * s_win[i + 1] : T(0);
+          // window pair (zero outside the window) in one aligned load; DIT pass: bit-reversed slots
+          C w2; w2.x = T(0); w2.y = T(0);
+          if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
+          re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
+          im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
         }
         warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
         sstts_cp_async_wait_all();
@@ -416,8 +433,9 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         const int m = 64 * n1 + 2 * lane;
         const int i = m - lpad;
         if (m >= mlo && m < lpad + win + 1) {
-          const T v0 = (i >= 0 && i < win) ? re[n1] * s_win[i] : T(0);
-          const T v1 = (i + 1 >= 0 && i + 1 < win) ? im[n1] * s_win[i + 1] : T(0);
+          const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
+          const T v0 = re[n1] * w2.x;
+          const T v1 = im[n1] * w2.y;
           typename cx_of<T>::type vv;
           vv.x = v0; vv.y = v1;
           *reinterpret_cast<typename cx_of<T>::type*>(plane + (m - mlo)) = vv;   // m - mlo is even
@@ -568,12 +586,11 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = s_tw + 1024;
   T* s_planes = reinterpret_cast<T*>(s_w2k + 512);
-  T* s_win = s_planes + W * FEAT_PLANE_ELEMS;
-  float* s_x = reinterpret_cast<float*>(s_win + round_up4(win));
+  T* s_win = load_window_table<T>(s_planes + W * FEAT_PLANE_ELEMS, A.tab.window, win, lpad, tid, W * 32);
+  float* s_x = reinterpret_cast<float*>(s_planes + W * FEAT_PLANE_ELEMS + round_up4(win + WIN_TAB_PAD));
 
   for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
-  for (int i = tid; i < win; i += NT) s_win[i] = A.tab.window[i];
   __syncthreads();
 
   // mel filterbank (CSR) in shared memory, after the sample span
@@ -646,8 +663,10 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
       for (int n1 = 0; n1 < 32; ++n1) {
         const int m = 64 * n1 + 2 * lane;
         const int i = m - lpad;
-        re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * s_win[i] : T(0);      // DIT pass: bit-reversed slots
-        im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * s_win[i + 1] : T(0);
+        C w2; w2.x = T(0); w2.y = T(0);
+        if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
+        re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * w2.x : T(0);      // DIT pass: bit-reversed slots
+        im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * w2.y : T(0);
       }
       warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
       float* s_mag = reinterpret_cast<float*>(plane);  // transpose plane is dead: |S| of this frame
@@ -756,7 +775,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
 template <typename T>
 SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_mels, int mel_nnz) {
   return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
-         sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win)) +
+         sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win + WIN_TAB_PAD)) +
          sizeof(float) * 2 * (size_t)round_up4(span_max) + sizeof(T) * (size_t)round_up4(mel_nnz) +
          sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
 }
