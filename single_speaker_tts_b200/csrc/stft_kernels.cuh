@@ -188,7 +188,10 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
 #define SSTTS_COLUMN_GATHER 1   // measured: 0.673 -> 0.656 ms per Griffin-Lim iteration launch
 #endif
 #ifndef SSTTS_COLUMN_STAGE
-#define SSTTS_COLUMN_STAGE 0
+#define SSTTS_COLUMN_STAGE 0      // measured slower (0.694 ms): needs a second pass for hop > NT
+#endif
+#ifndef SSTTS_STAGE_BATCH
+#define SSTTS_STAGE_BATCH 1       // measured: 0.656 -> 0.632 ms per Griffin-Lim iteration launch
 #endif
 constexpr int MAX_OVERLAP = 5;  // frames covering one sample: ceil(win / hop) <= 5 (host_plan.h)
 constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
@@ -403,6 +406,32 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
     if (plain) {
       const T* own = pin_own + span_lo;
       const T* oth = pin_oth + span_lo;
+#if SSTTS_STAGE_BATCH
+      // all global loads of the thread first (independent, in flight together), then the stores;
+      // residue of sample s: (span_lo - lpad + s) mod hop = s mod hop since span_lo - lpad = a hop
+      constexpr int NS = W + MAX_OVERLAP - 1;
+      T x[NS], e[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int s = tid + i * NT;
+        x[i] = s < span ? own[s] : T(0);
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int s = tid + i * NT;
+        e[i] = (s < span && (s < le || s >= rb)) ? oth[s] : T(0);
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int s = tid + i * NT;
+        if (s < span) s_yin[s] = (x[i] + e[i]) * s_rw[s % hop];
+      }
+      for (int s = tid + NS * NT; s < span; s += NT) {   // spans longer than NS * NT (run-time geometry)
+        T v = own[s];
+        if (s < le || s >= rb) v += oth[s];
+        s_yin[s] = v * s_rw[s % hop];
+      }
+#else
       int r = tid % hop;                 // (span_lo - lpad + s) mod hop with span_lo - lpad = a * hop
 #pragma unroll 4
       for (int s = tid; s < span; s += NT) {
@@ -412,6 +441,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         r += NT;
         if (r >= hop) r %= hop;
       }
+#endif
 #endif
     } else {
       for (int s = tid; s < span; s += NT) {
