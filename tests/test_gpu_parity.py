@@ -254,3 +254,32 @@ def test_trim_batch_matches_oracle():
         yr, br = lc.trim(w)
         assert tuple(b) == tuple(br) and np.array_equal(t, yr)
         assert tuple(effects.trim(w)[1]) == tuple(br)
+
+
+def test_file_level_drivers_precalc_and_statistics(tmp_path):
+    """tacotron/dataset_precalc_features.py and dataset_statistics.py paths end to end on wav files:
+    pre_compute_features (datasets/dataset_helper.py:326-355) writes <name>.npz with mel_mag_db /
+    linear_mag_db, collect_decibel_statistics (datasets/statistics.py:69-98) averages per-file extrema."""
+    from scipy.io import wavfile
+    from single_speaker_tts_b200.audio.io import load_wav
+    rng = np.random.default_rng(21)
+    paths = []
+    for i, n in enumerate((30000, 12000, 50000)):
+        x = np.concatenate([np.zeros(3000, np.float32), speech_like_clip(n, rng), np.zeros(2000, np.float32)])
+        path = str(tmp_path / ('clip%d.wav' % i))
+        wavfile.write(path, 22050, (x * 32767).astype(np.int16))
+        paths.append(path)
+    LJSpeechDatasetHelper.pre_compute_features(paths, batch_clips=2)
+    for path in paths:
+        wav, sr = load_wav(path)
+        assert sr == 22050 and wav.dtype == np.float32
+        mel_ref, lin_ref = ra.load_audio_from_wav(wav, sr, trim=True)
+        data = np.load(path[:-4] + '.npz')
+        assert data['mel_mag_db'].shape == mel_ref.shape and data['linear_mag_db'].shape == lin_ref.shape
+        assert np.abs(data['mel_mag_db'] - mel_ref).max() <= NORM_TOL
+        assert np.abs(data['linear_mag_db'] - lin_ref).max() <= NORM_TOL
+        mel, lin = LJSpeechDatasetHelper.load_audio(path.encode())
+        assert np.array_equal(mel, data['mel_mag_db']) and np.array_equal(lin, data['linear_mag_db'])
+    stats = statistics.collect_decibel_statistics(paths, batch_clips=2)
+    ref = ra.collect_decibel_statistics_from_wavs([load_wav(p)[0] for p in paths], 22050)
+    assert np.abs(stats - ref).max() < 1e-3
