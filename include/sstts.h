@@ -94,6 +94,8 @@ int sstts_griffin_lim(const sstts_gl_plan* plan, const float* mag_dev, const flo
 /* Fill n unit phasors exp(2 pi i u), u ~ U[0, 1) from a counter-based generator keyed by seed
  * (batched extension: replaces the host-side np.random.rand of audio/synthesis.py:85). */
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream);
+/* Same stream of phasors, starting at element `first` (so a batch can be filled in pieces). */
+int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_dev, void* stream);
 
 /* Call-site glue in front of Griffin-Lim -- replaces tacotron/inference.py:94-101,175 (and
  * tacotron/serve.py:42-59): audio/conversion.py:81-102 `inv_normalize_decibel`, :32-53

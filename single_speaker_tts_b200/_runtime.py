@@ -101,6 +101,34 @@ def _offsets(counts):
 # ----------------------------------------------------------------------------------------------
 # Griffin-Lim
 # ----------------------------------------------------------------------------------------------
+# Batches above this many frames are split into sub-batches whose uploads overlap the previous
+# sub-batch's iterations (copy stream + events); results do not depend on the split.
+_GL_CHUNK_FRAMES = 24000
+_copy_streams = threading.local()
+
+
+def _copy_stream(dev):
+    d = getattr(_copy_streams, 'd', None)
+    if d is None:
+        d = _copy_streams.d = {}
+    if dev.index not in d:
+        d[dev.index] = torch.cuda.Stream(device=dev)
+    return d[dev.index]
+
+
+def _split_by_frames(frames, limit):
+    """Contiguous index ranges of roughly `limit` frames each."""
+    ranges, i0, acc = [], 0, 0
+    for i, t in enumerate(frames):
+        acc += t
+        if acc >= limit:
+            ranges.append((i0, i + 1))
+            i0, acc = i + 1, 0
+    if i0 < len(frames):
+        ranges.append((i0, len(frames)))
+    return ranges
+
+
 def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
                       precision='f32', return_mse=False, device=None, denormalize=None):
     """Griffin-Lim for a ragged batch (reference: audio/synthesis.py:43-125, one call per item).
@@ -115,6 +143,10 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
              tacotron/inference.py:94-101,175 (inv_normalize_decibel -> decibel_to_magnitude ->
              ** power) runs fused on the device before the first iteration.
     Returns (list of float32 waveforms of length hop*(T_i-1), list of mse floats or None).
+
+    Large batches are processed as a pipeline of sub-batches: while sub-batch k iterates on the
+    compute stream, the host packs sub-batch k + 1 into pinned memory and its H2D copy runs on a
+    copy stream.
     """
     lib = _lib.load()
     dev = require_cuda(device)
@@ -133,68 +165,95 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         frames.append(m.shape[1])
     if return_mse and n_iter < 1:
         raise ValueError('mse needs n_iter >= 1')
-    frame_off = _offsets(frames)
+    if angles is not None:
+        if len(angles) != n:
+            raise ValueError('need one initial phase array per spectrogram')
+        for a, m in zip(angles, mags):
+            if a.shape != m.shape:
+                raise ValueError('initial phase shape {} != spectrogram shape {}'.format(a.shape, m.shape))
+    elif seed is None:
+        seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
     cfg = _make_config(n_fft, win_length, hop_length, precision)
-    key = (dev.index, n_fft, win_length, hop_length, cfg.precision, frame_off.tobytes())
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    ranges = _split_by_frames(frames, _GL_CHUNK_FRAMES)
+    frame_base = _offsets(frames)
 
-    def factory():
-        h = ctypes.c_void_p()
-        with torch.cuda.device(dev):
-            _lib.check(lib.sstts_gl_plan_create(ctypes.byref(cfg), n,
-                                                frame_off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                                ctypes.byref(h)))
-        return _Plan(h, lib.sstts_gl_plan_destroy)
+    def get_plan(i0, i1):
+        fo = _offsets(frames[i0:i1])
+        key = (dev.index, n_fft, win_length, hop_length, cfg.precision, fo.tobytes())
 
-    plan = _gl_plans.get(key, factory)
-    total_frames = int(frame_off[-1])
-    total_samples = int(lib.sstts_gl_total_samples(plan.handle))
-    sample_off = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(n + 1,)).copy()
+        def factory():
+            h = ctypes.c_void_p()
+            with torch.cuda.device(dev):
+                _lib.check(lib.sstts_gl_plan_create(ctypes.byref(cfg), i1 - i0, fo.ctypes.data_as(i64p),
+                                                    ctypes.byref(h)))
+            return _Plan(h, lib.sstts_gl_plan_destroy)
+
+        return _gl_plans.get(key, factory), fo
 
     with torch.cuda.device(dev):
-        mag_dev = _hostio.upload_rows([m.T for m in mags], n_bins, torch.float32, dev, slot='mag')
-        flag_dev = None
-        if denormalize is not None:
-            ref_db, max_db, power = [float(v) for v in denormalize]
-            flag_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-            _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), total_frames * n_bins, ref_db, max_db,
-                                                       power, _ptr(mag_dev), _ptr(flag_dev), _stream_ptr()))
-        if angles is not None:
-            if len(angles) != n:
-                raise ValueError('need one initial phase array per spectrogram')
-            blocks = []
-            for a, m in zip(angles, mags):
-                if a.shape != m.shape:
-                    raise ValueError('initial phase shape {} != spectrogram shape {}'.format(a.shape, m.shape))
-                blocks.append(np.asarray(a).T)
-            phase_dev = torch.view_as_real(_hostio.upload_rows(blocks, n_bins, torch.complex64, dev, slot='phase'))
-        else:
-            if seed is None:
-                seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
-            phase_dev = torch.empty((total_frames, n_bins, 2), dtype=torch.float32, device=dev)
-            _lib.check(lib.sstts_random_phase(ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
-                                              total_frames * n_bins, _ptr(phase_dev), _stream_ptr()))
-        ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan.handle)), dtype=torch.uint8, device=dev)
-        wav_dev = torch.empty(max(total_samples, 1), dtype=torch.float32, device=dev)
-        mse_dev = torch.zeros(total_frames, dtype=torch.float64, device=dev) if return_mse else None
-        _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
-                                         _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
-        wav_np = _hostio.download(wav_dev)
-        mf = _hostio.download(mse_dev) if return_mse else None
+        main = torch.cuda.current_stream()
+        copy = _copy_stream(dev) if len(ranges) > 1 else main
+
+        def upload(k):
+            """Pack + H2D of sub-batch k on the copy stream; returns device tensors and an event."""
+            i0, i1 = ranges[k]
+            with torch.cuda.stream(copy):
+                mag_dev = _hostio.upload_rows([m.T for m in mags[i0:i1]], n_bins, torch.float32, dev,
+                                              slot='mag%d' % (k & 1))
+                ph_dev = None
+                if angles is not None:
+                    ph_dev = torch.view_as_real(_hostio.upload_rows(
+                        [np.asarray(a).T for a in angles[i0:i1]], n_bins, torch.complex64, dev,
+                        slot='phase%d' % (k & 1)))
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return mag_dev, ph_dev, ev
+
+        flag_dev = torch.zeros(1, dtype=torch.int32, device=dev) if denormalize is not None else None
+        outs = []
+        nxt = upload(0)
+        for k, (i0, i1) in enumerate(ranges):
+            mag_dev, phase_dev, ev = nxt
+            plan, fo = get_plan(i0, i1)
+            tf = int(fo[-1])
+            main.wait_event(ev)
+            # tensors allocated on the copy stream are consumed on the compute stream
+            mag_dev.record_stream(main)
+            if phase_dev is not None:
+                phase_dev.record_stream(main)
+            if denormalize is not None:
+                ref_db, max_db, power = [float(v) for v in denormalize]
+                _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), tf * n_bins, ref_db, max_db, power,
+                                                           _ptr(mag_dev), _ptr(flag_dev), _stream_ptr()))
+            if phase_dev is None:
+                phase_dev = torch.empty((tf, n_bins, 2), dtype=torch.float32, device=dev)
+                _lib.check(lib.sstts_random_phase_at(ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                                     int(frame_base[i0]) * n_bins, tf * n_bins,
+                                                     _ptr(phase_dev), _stream_ptr()))
+            ts = int(lib.sstts_gl_total_samples(plan.handle))
+            so = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(i1 - i0 + 1,)).copy()
+            ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan.handle)), dtype=torch.uint8, device=dev)
+            wav_dev = torch.empty(max(ts, 1), dtype=torch.float32, device=dev)
+            mse_dev = torch.zeros(tf, dtype=torch.float64, device=dev) if return_mse else None
+            _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
+                                             _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
+            outs.append((_hostio.download(wav_dev), _hostio.download(mse_dev) if return_mse else None, so, fo))
+            if k + 1 < len(ranges):
+                nxt = upload(k + 1)          # host packing + H2D overlap the iterations just enqueued
         flag = _hostio.download(flag_dev) if flag_dev is not None else None
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
     if flag is not None and int(flag[0]) != 0:
         # same error as the reference's decibel_to_magnitude (audio/conversion.py:47-49)
         raise AssertionError('"conversion.decibel_to_magnitude" was asked to convert a dB value '
                              'smaller -100 dB.')
-    wavs = [wav_np[sample_off[i]:sample_off[i + 1]] for i in range(n)]
-    mses = None
-    if return_mse:
-        mses = []
-        for i in range(n):
-            if frames[i] < 2:
-                mses.append(None)
-            else:
-                mses.append(float(mf[frame_off[i]:frame_off[i + 1]].sum() / (n_bins * frames[i])))
+    wavs, mses = [], ([] if return_mse else None)
+    for (wav_np, mf, so, fo), (i0, i1) in zip(outs, ranges):
+        for j in range(i1 - i0):
+            wavs.append(wav_np[so[j]:so[j + 1]])
+            if return_mse:
+                t = frames[i0 + j]
+                mses.append(None if t < 2 else float(mf[fo[j]:fo[j + 1]].sum() / (n_bins * t)))
     return wavs, mses
 
 

@@ -284,11 +284,11 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
 }
 
 // counter-based uniform phase: splitmix64 of (seed, index) -> 24-bit uniform -> unit phasor
-__global__ void random_phase_kernel(unsigned long long seed, long long n, float2* out) {
+__global__ void random_phase_kernel(unsigned long long seed, long long first, long long n, float2* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(first + i + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     z = z ^ (z >> 31);
@@ -407,15 +407,19 @@ int sstts_griffin_lim(const sstts_gl_plan* P, const float* mag_dev, const float*
                                                          wav_out_dev, mse_frame_dev, st);
 }
 
-int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
-  if (n < 0 || (n > 0 && !phase_dev)) return fail(SSTTS_ERR_INVALID, "bad random_phase arguments");
+int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_dev, void* stream) {
+  if (n < 0 || first < 0 || (n > 0 && !phase_dev)) return fail(SSTTS_ERR_INVALID, "bad random_phase arguments");
   if (n == 0) return 0;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   random_phase_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      seed, n, reinterpret_cast<float2*>(phase_dev));
+      seed, first, n, reinterpret_cast<float2*>(phase_dev));
   CU(cudaGetLastError());
   return 0;
+}
+
+int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
+  return sstts_random_phase_at(seed, 0, n, phase_dev, stream);
 }
 
 int sstts_denormalize_magnitude(const float* norm_dev, int64_t n, double ref_db, double max_db,

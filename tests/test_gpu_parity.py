@@ -112,6 +112,22 @@ def test_griffin_lim_batch_invariance_and_layouts():
     assert np.array_equal(w64, batch[0])
 
 
+def test_griffin_lim_sub_batch_pipeline_is_invisible(monkeypatch):
+    """Large batches run as a pipeline of sub-batches (copy stream + events): neither the explicit-
+    phase nor the seeded-device-phase results may depend on where the batch is split."""
+    from single_speaker_tts_b200 import _runtime
+    mags, angs = _case([40, 9, 100, 17, 64, 3])
+    whole = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 4, angles=angs)
+    whole_seeded, mse_whole = _runtime.griffin_lim_batch(mags, WIN, HOP, NFFT, 4, seed=99, return_mse=True)
+    monkeypatch.setattr(_runtime, '_GL_CHUNK_FRAMES', 50)
+    assert len(_runtime._split_by_frames([m.shape[1] for m in mags], 50)) > 2
+    split = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 4, angles=angs)
+    split_seeded, mse_split = _runtime.griffin_lim_batch(mags, WIN, HOP, NFFT, 4, seed=99, return_mse=True)
+    for a, b, c, d in zip(whole, split, whole_seeded, split_seeded):
+        assert np.array_equal(a, b) and np.array_equal(c, d)
+    assert mse_whole == mse_split
+
+
 def test_griffin_lim_dynamic_geometry_and_zero_bins():
     win, hop = 1024, 256
     x = speech_like_clip(hop * 40 + 3, np.random.default_rng(8))
