@@ -1,5 +1,5 @@
 """Hot spots of one kernel from an ncu report (SASS view):
-   python tools/ncu_hot.py report.ncu-rep <kernel regex> [top]"""
+   python tools/ncu_hot.py report.ncu-rep <kernel regex> [top] [launch-skip]"""
 import csv
 import io
 import subprocess
@@ -7,8 +7,9 @@ import sys
 
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+skip = sys.argv[4] if len(sys.argv) > 4 else '0'
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + pat,
-                      '--launch-count', '1'], capture_output=True, text=True).stdout
+                      '--launch-skip', skip, '--launch-count', '1'], capture_output=True, text=True).stdout
 lines = raw.splitlines()
 rows = list(csv.reader(io.StringIO('\n'.join(lines[1:]))))
 h = rows[0]

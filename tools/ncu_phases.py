@@ -3,7 +3,7 @@ stall samples per phase:  python tools/ncu_phases.py report.ncu-rep <kernel rege
 import csv, io, subprocess, sys
 rep, pat = sys.argv[1], sys.argv[2]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + pat,
-                      '--launch-count', '1'], capture_output=True, text=True).stdout
+                      '--launch-skip', (sys.argv[3] if len(sys.argv) > 3 else '0'), '--launch-count', '1'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO('\n'.join(raw.splitlines()[1:]))))
 h = rows[0]
 isrc, isamp, iex = h.index('Source'), h.index('# Samples'), h.index('Instructions Executed')
