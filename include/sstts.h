@@ -143,6 +143,9 @@ typedef struct sstts_feat_outputs {
   int normalize;       /* apply audio/conversion.py:78 with the constants below                */
   double lin_ref_db, lin_max_db, mel_ref_db, mel_max_db;
   double mel_power;    /* audio/features.py:71 `power` */
+  int force_generic;   /* 0: the library picks the fused dB-feature kernel mode when the request is
+                          lin_db + mel_db only (n_fft 2048, power 1); 1: always the generic mode
+                          (validation / A-B runs; results agree to float32 rounding)              */
 } sstts_feat_outputs;
 
 int sstts_stft_features(const sstts_feat_plan* plan, const float* wav_dev,

@@ -35,7 +35,7 @@ class FeatOutputs(ctypes.Structure):
                 ('minmax_dev', ctypes.c_void_p), ('normalize', ctypes.c_int),
                 ('lin_ref_db', ctypes.c_double), ('lin_max_db', ctypes.c_double),
                 ('mel_ref_db', ctypes.c_double), ('mel_max_db', ctypes.c_double),
-                ('mel_power', ctypes.c_double)]
+                ('mel_power', ctypes.c_double), ('force_generic', ctypes.c_int)]
 
 
 # name -> (restype, argtypes); also the list the symbol-export test checks against the header.

@@ -286,7 +286,7 @@ class FeatureBatch:
 def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None, n_mels=0, fmin=0.0,
                         fmax=None, reduction=1, want_spec=False, want_lin=False, want_mel=False,
                         want_mel_raw=False, want_minmax=False, normalize=None, power=1.0,
-                        precision='f64', device=None, keep_on_device=False, trim=None):
+                        precision='f64', device=None, keep_on_device=False, trim=None, force_generic=False):
     """Batched STFT -> |.| -> linear / mel -> dB -> (0,1) pipeline on the GPU.
 
     normalize: None (raw dB) or (lin_ref_db, lin_max_db, mel_ref_db, mel_max_db) as in
@@ -295,6 +295,8 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     trim: None, or ``(top_db, frame_length, hop_length)``: silence-trim every clip on the device
     first (librosa.effects.trim as called at datasets/lj_speech.py:119); the features are computed
     on the trimmed part of the same upload and ``result.trim_bounds`` holds (start, end) per clip.
+    force_generic: run the kernel's generic mode even where the fused dB-feature mode applies (lin +
+    mel dB only, n_fft 2048, power 1) -- for validation; the two agree to float32 rounding.
     """
     lib = _lib.load()
     dev = require_cuda(device)
@@ -372,6 +374,7 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
         if normalize is not None:
             out.lin_ref_db, out.lin_max_db, out.mel_ref_db, out.mel_max_db = [float(v) for v in normalize]
         out.mel_power = float(power)
+        out.force_generic = 1 if force_generic else 0
         _lib.check(lib.sstts_stft_features(plan.handle, _ptr(wav_dev), ctypes.byref(out), _stream_ptr()))
         if keep_on_device:
             res.spec = torch.view_as_complex(spec_dev) if want_spec else None

@@ -72,6 +72,7 @@ inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int h
     split_frames((int)T, kTileFrames, min_tile, parts);
     for (size_t i = 0; i < parts.size(); ++i) {
       GLTile t; t.utt = u; t.a = parts[i].first; t.b = parts[i].second; t.parity = (int)(i & 1);
+      t.f0 = frame_off[u]; t.poff = P.pad_off[u]; t.n_frames = (int)T; t.reserved = 0; t.soff = P.sample_off[u];
       P.tiles.push_back(t);
       const int ft = t.b - t.a;
       if (ft > P.max_tile) P.max_tile = ft;
@@ -193,6 +194,44 @@ inline void make_mel_csr(int sr, int n_fft, int n_mels, double fmin, double fmax
     M.ptr.push_back((int)M.w.size());
     if (dense) for (int k = 0; k < n_bins; ++k) (*dense)[(size_t)i * n_bins + k] = row[k];
   }
+}
+
+// The filterbank padded for the kernel's dB-feature mode: slot j holds the filters
+// m = mbase[j] + lane (top 32 filters first -- filter lengths grow with m, so a slot's filters have
+// similar lengths); w[woff[j] + 32 * i + lane] is element i of filter m, zero beyond its support.
+// ok == false when the layout does not fit the kernel's limits (then the generic mode is used).
+struct MelPadded {
+  int n_slots = 0, total = 0;
+  int len[4] = {0, 0, 0, 0}, woff[4] = {0, 0, 0, 0}, mbase[4] = {0, 0, 0, 0};
+  std::vector<float> w;
+  bool ok = false;
+};
+inline void make_mel_padded(const MelCSR& M, int n_mels, int mag_elems, MelPadded& P) {
+  P = MelPadded();
+  if (n_mels < 1 || n_mels > 128) return;
+  P.n_slots = (n_mels + 31) / 32;
+  for (int j = 0; j < P.n_slots; ++j) {
+    P.mbase[j] = n_mels - 32 * (j + 1);
+    int L = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int m = P.mbase[j] + l;
+      if (m < 0 || m >= n_mels) continue;
+      const int n = M.ptr[m + 1] - M.ptr[m];
+      if (n > L) L = n;
+    }
+    P.len[j] = L;
+    P.woff[j] = P.total;
+    P.total += 32 * L;
+  }
+  P.w.assign((size_t)P.total, 0.0f);
+  for (int j = 0; j < P.n_slots; ++j)
+    for (int l = 0; l < 32; ++l) {
+      const int m = P.mbase[j] + l;
+      if (m < 0 || m >= n_mels) continue;
+      if (M.k0[m] + P.len[j] > mag_elems) return;    // padded reads would leave the |S| plane
+      for (int i = M.ptr[m]; i < M.ptr[m + 1]; ++i) P.w[(size_t)P.woff[j] + 32 * (i - M.ptr[m]) + l] = (float)M.w[i];
+    }
+  P.ok = P.total > 0;
 }
 
 }  // namespace sstts

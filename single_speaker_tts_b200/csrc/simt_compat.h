@@ -32,6 +32,11 @@ __device__ __forceinline__ void sstts_cp_async_wait_group1() {
 }
 // SFU log2 (MUFU.LG2) and square root (MUFU.SQRT), max relative error ~2^-22
 __device__ __forceinline__ float sstts_log2_approx(float x) { return __log2f(x); }
+__device__ __forceinline__ float sstts_log2_ftz(float x) {       // bare MUFU.LG2 (x is never subnormal here)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float sstts_rsqrt_approx(float x) {   // MUFU.RSQ, denormals flushed
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

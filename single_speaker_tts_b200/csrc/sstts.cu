@@ -143,6 +143,7 @@ struct sstts_feat_plan {
   FeatPlanHost host;
   DeviceTables tab;
   MelCSR mel;
+  MelPadded melp;
   std::vector<double> mel_dense;
   long long* d_sample_off = nullptr;
   long long* d_sample_len = nullptr;
@@ -152,6 +153,7 @@ struct sstts_feat_plan {
   int* d_mel_ptr = nullptr;
   int* d_mel_k0 = nullptr;
   void* d_mel_w = nullptr;
+  float* d_melp_w = nullptr;
   int device = 0;
   int n_sms = 0;
 };
@@ -361,9 +363,20 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   A.n_fft = P->cfg.n_fft;
   if (A.n_mels < 1) { A.mel_out = nullptr; A.melraw_out = nullptr; }
 
-  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max, P->cfg.n_mels, (int)P->mel.w.size());
+  // the pre-calculation configuration runs the fused dB-feature mode of the kernel
+  const bool fast = P->melp.ok && P->d_melp_w && A.n_fft == NFFT && A.lin_out && A.mel_out && !A.spec_out &&
+                    !A.melraw_out && !A.minmax_out && A.mel_power == 1.0f && !O->force_generic;
+  A.melp_w = P->d_melp_w;
+  A.melp_slots = fast ? P->melp.n_slots : 0;
+  A.melp_total = fast ? P->melp.total : 0;
+  for (int j = 0; j < 4; ++j) { A.melp_len[j] = P->melp.len[j]; A.melp_woff[j] = P->melp.woff[j]; A.melp_mbase[j] = P->melp.mbase[j]; }
+
+  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max, P->cfg.n_mels, (int)P->mel.w.size(),
+                                                 A.melp_total);
+  auto kernel = fast ? stft_feature_kernel<T, G, W, FeatMode::kDbFeatures>
+                     : stft_feature_kernel<T, G, W, FeatMode::kGeneric>;
   int occ = 0, rc;
-  if ((rc = configure_kernel(stft_feature_kernel<T, G, W>, W * 32, smem, &occ))) return rc;
+  if ((rc = configure_kernel(kernel, W * 32, smem, &occ))) return rc;
   const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
   int grid = n_sms * occ;
   if (grid > A.n_tiles) grid = A.n_tiles;
@@ -372,7 +385,7 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
     minmax_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(A.minmax_out, H.n_clips);
     CU(cudaGetLastError());
   }
-  stft_feature_kernel<T, G, W><<<grid, W * 32, smem, st>>>(A);
+  kernel<<<grid, W * 32, smem, st>>>(A);
   CU(cudaGetLastError());
   if (A.minmax_out) {
     const int n = H.n_clips * 4;
@@ -461,8 +474,10 @@ int sstts_feat_plan_create_ranges(const sstts_stft_config* cfg, int n_clips, con
     if (cfg->sampling_rate < 1) { sstts_feat_plan_destroy(P); return fail(SSTTS_ERR_INVALID, "sampling_rate must be > 0"); }
     const double fmax = cfg->mel_fmax > 0 ? cfg->mel_fmax : cfg->sampling_rate / 2.0;
     make_mel_csr(cfg->sampling_rate, cfg->n_fft, cfg->n_mels, cfg->mel_fmin, fmax, P->mel, &P->mel_dense);
+    make_mel_padded(P->mel, cfg->n_mels, FEAT_PLANE_ELEMS, P->melp);
     rc = upload(P->mel.ptr, &P->d_mel_ptr);
     if (!rc) rc = upload(P->mel.k0, &P->d_mel_k0);
+    if (!rc && P->melp.ok) rc = upload(P->melp.w, &P->d_melp_w);
     if (!rc) {
       if (f64) { double* d; rc = upload(P->mel.w, &d); P->d_mel_w = d; }
       else { std::vector<float> wf(P->mel.w.begin(), P->mel.w.end()); float* d; rc = upload(wf, &d); P->d_mel_w = d; }
@@ -506,7 +521,7 @@ void sstts_feat_plan_destroy(sstts_feat_plan* P) {
   P->tab.release();
   cudaFree(P->d_sample_off); cudaFree(P->d_sample_len); cudaFree(P->d_frame_off); cudaFree(P->d_row_off);
   cudaFree(P->d_tiles);
-  cudaFree(P->d_mel_ptr); cudaFree(P->d_mel_k0); cudaFree(P->d_mel_w);
+  cudaFree(P->d_mel_ptr); cudaFree(P->d_mel_k0); cudaFree(P->d_mel_w); cudaFree(P->d_melp_w);
   delete P;
 }
 

@@ -151,7 +151,14 @@ SSTTS_D T normalise_ola(T v, int p, int n_frames, int hop, int win, int lpad, co
 // =============================================================================================
 // Griffin-Lim
 // =============================================================================================
-struct GLTile { int utt, a, b, parity; };  // frames [a, b) of utterance utt, b - a <= 8
+// frames [a, b) of utterance utt, b - a <= 8.  The record carries the utterance's offsets so that a
+// kernel needs ONE independent 48-byte load per tile instead of a tile -> utterance -> offsets chain.
+struct alignas(16) GLTile {
+  int utt, a, b, parity;
+  long long f0, poff;        // frame_off[utt], pad_off[utt]
+  int n_frames, reserved;    // frames of the utterance
+  long long soff;            // sample_off[utt]
+};
 
 template <typename T> struct GLArgs {
   const float* mag;              // (sum T, 1025) frame-major |S|
@@ -347,16 +354,14 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
   __syncthreads();
 
-  // Tile descriptor, loaded one tile ahead so that the dependent global loads
-  // (tile -> utterance -> offsets) are hidden behind the transform of the current tile.
+  // Tile record, loaded one tile ahead (one independent 48-byte load hidden behind the transform
+  // of the current tile).
   struct TileCtx { int a, b, parity, n_frames; long long f0, poff; };
   auto load_ctx = [&](int t) {
     TileCtx c;
     const GLTile tl = A.tiles[t];
     c.a = tl.a; c.b = tl.b; c.parity = tl.parity;
-    c.f0 = A.frame_off[tl.utt];
-    c.n_frames = (int)(A.frame_off[tl.utt + 1] - c.f0);
-    c.poff = A.pad_off[tl.utt];
+    c.f0 = tl.f0; c.n_frames = tl.n_frames; c.poff = tl.poff;
     return c;
   };
 
@@ -648,6 +653,12 @@ template <typename T> struct FeatArgs {
   const int* mel_k0;              // [n_mels]     first FFT bin of each mel filter
   const T* mel_w;                 // [nnz]        filter weights (float64 -> T)
   int n_mels, mel_nnz;
+  // the same filterbank padded for the fused dB-feature mode (FeatMode::kDbFeatures): slot j holds
+  // the filters m = melp_mbase[j] + lane (32 per slot, top filters first); element i of filter m is
+  // melp_w[melp_woff[j] + 32 * i + lane], zero beyond the filter's support, i < melp_len[j]
+  const float* melp_w;
+  int melp_slots, melp_total;
+  int melp_len[4], melp_woff[4], melp_mbase[4];
   float2* spec_out;               // (rows, 1025) complex64 STFT, or nullptr
   float* lin_out;                 // (rows, 1025) linear dB (normalised if normalize), or nullptr
   float* mel_out;                 // (rows, n_mels) mel dB (normalised if normalize), or nullptr
@@ -680,8 +691,18 @@ SSTTS_D long long encode_ordered(double v) {
 
 constexpr int FEAT_PLANE_ELEMS = 1056;  // >= XPLANE_ELEMS and >= NBINS floats
 
-template <typename T, typename G, int W>
+// MODE = FeatMode::kGeneric: every output is optional and selected at run time.
+// MODE = FeatMode::kDbFeatures: the pre-calculation configuration (datasets/lj_speech.py:106-156) --
+// linear dB + mel dB (power 1), optionally normalised, n_fft = 2048, nothing else: the dB / normalise
+// chain collapses to max -> MUFU.LG2 -> one FFMA -> clamp per bin (the transform's factor 2 and the
+// dB scale are folded into the FFMA constants), the mel projection runs in float32 over a padded,
+// lane-per-filter table without index arithmetic, and the staging of interior tiles uses 16-byte
+// copies.  Results differ from kGeneric by float32 rounding only (~1e-7 of the normalised value).
+struct FeatMode { enum { kGeneric = 0, kDbFeatures = 1 }; };
+
+template <typename T, typename G, int W, int MODE>
 __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> A) {
+  constexpr bool FAST = MODE == FeatMode::kDbFeatures;
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, A.n_fft);
   const int win = g.win(), hop = g.hop(), lpad = g.lpad(), cpad = g.cpad();
@@ -701,13 +722,22 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
   __syncthreads();
 
-  // mel filterbank (CSR) in shared memory, after the sample span
-  T* s_mel_w = reinterpret_cast<T*>(s_x + 2 * round_up4(A.span_max));
+  // mel filterbank in shared memory, after the two sample-span buffers: CSR (generic mode) or the
+  // padded lane-per-filter table (dB-feature mode)
+  const int xbuf_elems = round_up4(A.span_max) + 8;     // + slack for the 16-byte staging shift
+  T* s_mel_w = reinterpret_cast<T*>(s_x + 2 * xbuf_elems);
   int* s_mel_ptr = reinterpret_cast<int*>(s_mel_w + round_up4(A.mel_nnz));
   int* s_mel_k0 = s_mel_ptr + round_up4(A.n_mels + 1);
-  for (int i = tid; i < A.mel_nnz; i += NT) s_mel_w[i] = A.mel_w[i];
-  for (int i = tid; i < A.n_mels; i += NT) { s_mel_ptr[i] = A.mel_ptr[i]; s_mel_k0[i] = A.mel_k0[i]; }
-  if (tid == 0 && A.n_mels > 0) s_mel_ptr[A.n_mels] = A.mel_ptr[A.n_mels];
+  float* s_melp_w = reinterpret_cast<float*>(s_x + 2 * xbuf_elems);
+  if (FAST) {
+    s_mel_k0 = reinterpret_cast<int*>(s_melp_w + round_up4(A.melp_total));
+    for (int i = tid; i < A.melp_total; i += NT) s_melp_w[i] = A.melp_w[i];
+    for (int i = tid; i < A.n_mels; i += NT) s_mel_k0[i] = A.mel_k0[i];
+  } else {
+    for (int i = tid; i < A.mel_nnz; i += NT) s_mel_w[i] = A.mel_w[i];
+    for (int i = tid; i < A.n_mels; i += NT) { s_mel_ptr[i] = A.mel_ptr[i]; s_mel_k0[i] = A.mel_k0[i]; }
+    if (tid == 0 && A.n_mels > 0) s_mel_ptr[A.n_mels] = A.mel_ptr[A.n_mels];
+  }
   __syncthreads();
 
   T* plane = s_planes + warp * FEAT_PLANE_ELEMS;
@@ -719,25 +749,45 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   const float lin_scale = 1.0f / A.lin_range_db, lin_shift = 1.0f - A.lin_ref_db / A.lin_range_db;
   const float mel_scale = (float)(1.0 / A.mel_range_db), mel_shift = (float)(1.0 - A.mel_ref_db / A.mel_range_db);
   const int pmode = A.mel_power == 1.0f ? 0 : (A.mel_power == 2.0f ? 1 : 2);
+  // dB-feature mode works on 2 X (|2 X|^2 = 4 |X|^2, mel of 2 |X|): value = log2(.) * a + b
+  const float fl_a = kDbPerLog2Pow * (A.normalize ? lin_scale : 1.0f);
+  const float fl_b = (A.normalize ? lin_shift : 0.0f) - 2.0f * fl_a;
+  const float fm_a = kDbPerLog2Mag * (A.normalize ? mel_scale : 1.0f);
+  const float fm_b = (A.normalize ? mel_shift : 0.0f) - fm_a;
+  const float clip_lo = A.normalize ? 0.0f : -3.0e38f, clip_hi = A.normalize ? 1.0f : 3.0e38f;
 
   // Sample spans are staged with 4-byte LDGSTS (reflect padding resolved per element) into a
   // double buffer: the span of the NEXT tile is in flight while the current tile is transformed.
-  float* s_xbuf[2] = {s_x, s_x + round_up4(A.span_max)};
-  auto issue_stage = [&](int t, float* buf) {
+  // Interior tiles (no reflection, >= 3 samples of the clip on both sides of the span) are copied in
+  // 16-byte chunks: the span starts `mis` floats past a 16-byte boundary of the packed wav buffer,
+  // so sample s lands at buf[s + mis]; issue_stage returns mis (0 for the per-element path).
+  float* s_xbuf[2] = {s_x, s_x + xbuf_elems};
+  auto issue_stage = [&](int t, float* buf) -> int {
     const FeatTile tl = A.tiles[t];
     const long long soff = A.sample_off[tl.clip];
     const int n_samples = (int)A.sample_len[tl.clip];
     const int span_lo = tl.a * hop + lpad;
     const int span = (tl.b - tl.a - 1) * hop + win;
     const float* x = A.wav + soff;
+    const int q0 = span_lo - cpad;
+    if (q0 >= 3 && q0 + span + 3 <= n_samples) {
+      const float* g = x + q0;
+      const int mis = (int)((reinterpret_cast<uintptr_t>(g) >> 2) & 3);
+      const float* gal = g - mis;
+      const int nch = (span + mis + 3) >> 2;
+      for (int c = tid; c < nch; c += NT) sstts_cp_async16(buf + 4 * c, gal + 4 * c);
+      return mis;
+    }
     for (int s = tid; s < span; s += NT) {
-      int q = span_lo + s - cpad;
+      int q = q0 + s;
       if (q < 0 || q >= n_samples) q = reflect_index(q, n_samples);
       sstts_cp_async4(buf + s, x + q);
     }
+    return 0;
   };
   int cur = 0;
-  if ((int)blockIdx.x < A.n_tiles) issue_stage(blockIdx.x, s_xbuf[0]);
+  int mis_cur = 0, mis_nxt = 0;
+  if ((int)blockIdx.x < A.n_tiles) mis_nxt = issue_stage(blockIdx.x, s_xbuf[0]);
   sstts_cp_async_commit();
 
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
@@ -751,7 +801,8 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
 
     sstts_cp_async_wait_all();    // this thread's part of the current span has landed
     __syncthreads();              // ... everyone's has, and the other buffer is no longer read
-    if (tile + (int)gridDim.x < A.n_tiles) issue_stage(tile + gridDim.x, s_xbuf[cur ^ 1]);
+    mis_cur = mis_nxt;
+    if (tile + (int)gridDim.x < A.n_tiles) mis_nxt = issue_stage(tile + gridDim.x, s_xbuf[cur ^ 1]);
     sstts_cp_async_commit();
     cur ^= 1;
     // zero rows appended by apply_reduction_padding (datasets/dataset_helper.py:383-393)
@@ -766,7 +817,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
     for (int jr = warp; jr < FT; jr += W) {
       const long long row = r0 + a + jr;
       T re[32], im[32];
-      const float* fin = s_xc + jr * hop - lpad;
+      const float* fin = s_xc + mis_cur + jr * hop - lpad;
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) {
         const int m = 64 * n1 + 2 * lane;
@@ -778,6 +829,7 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
       }
       warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
       float* s_mag = reinterpret_cast<float*>(plane);  // transpose plane is dead: |S| of this frame
+      float* lin_row = FAST ? A.lin_out + row * NBINS : nullptr;
       const int partner = (32 - lane) & 31;
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
@@ -795,6 +847,19 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
         const T dr = zr - pr, di = zi + pi;
         const T wor = w.x * di + w.y * dr;
         const T woi = w.y * di - w.x * dr;
+        if (FAST) {
+          // 2 X[k], 2 X[N-k] rounded to float32 (an exact power-of-two multiple of the complex64
+          // value librosa stores); |2 X|^2 -> 2 |X| for the mel projection and the fused dB value
+          const float fkr = (float)(er + wor), fki = (float)(ei + woi);
+          const float fnr = (float)(er - wor), fni = (float)(woi - ei);
+          const float pk = fmaf(fkr, fkr, fki * fki), pn = fmaf(fnr, fnr, fni * fni);
+          s_mag[k] = sstts_sqrt_approx(pk);
+          s_mag[kn] = sstts_sqrt_approx(pn);
+          const float lk = sstts_log2_ftz(fmaxf(4e-10f, pk)), ln = sstts_log2_ftz(fmaxf(4e-10f, pn));
+          lin_row[k] = fminf(fmaxf(fmaf(lk, fl_a, fl_b), clip_lo), clip_hi);
+          lin_row[kn] = fminf(fmaxf(fmaf(ln, fl_a, fl_b), clip_lo), clip_hi);
+          continue;
+        }
         const T xkr = T(0.5) * (er + wor), xki = T(0.5) * (ei + woi);   // X[k]
         const T xnr = T(0.5) * (er - wor), xni = T(0.5) * (woi - ei);   // X[N-k]
         if ((k & bmask) == 0) {   // kn = 1024 - k shares k's residue
@@ -819,6 +884,40 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
             }
           }
         }
+      }
+      if (FAST) {
+        if (lane == 0) {   // k = 512: X = conj(Z); keep the 2 X convention of the pair loop
+          const float fr = 2.0f * (float)re[16], fi = 2.0f * (float)im[16];
+          const float ph = fmaf(fr, fr, fi * fi);
+          s_mag[HALF / 2] = sstts_sqrt_approx(ph);
+          lin_row[HALF / 2] = fminf(fmaxf(fmaf(sstts_log2_ftz(fmaxf(4e-10f, ph)), fl_a, fl_b), clip_lo), clip_hi);
+        } else {
+          s_mag[NBINS - 1 + lane] = 0.0f;   // zero slack read (times zero weights) by padded filters
+        }
+        __syncwarp();
+        // mel_basis @ |S| in float32: lane = filter, padded weights [i][lane] (conflict-free), |S|
+        // taken from this warp's plane; all terms are >= 0, so float32 accumulation is accurate to
+        // ~n eps (1e-6 relative, 1e-5 dB)
+        float* mel_row = A.mel_out + row * A.n_mels;
+        for (int j = 0; j < A.melp_slots; ++j) {
+          const int m = A.melp_mbase[j] + lane;
+          const bool valid = m >= 0 && m < A.n_mels;
+          const float* wp = s_melp_w + A.melp_woff[j] + lane;
+          const float* mg = s_mag + (valid ? s_mel_k0[m] : 0);
+          const int len = A.melp_len[j];
+          float acc0 = 0.0f, acc1 = 0.0f;
+          int i = 0;
+#pragma unroll 4
+          for (; i + 1 < len; i += 2) {
+            acc0 = fmaf(wp[32 * i], mg[i], acc0);
+            acc1 = fmaf(wp[32 * i + 32], mg[i + 1], acc1);
+          }
+          if (i < len) acc0 = fmaf(wp[32 * i], mg[i], acc0);
+          const float lm = sstts_log2_ftz(fmaxf(2e-5f, acc0 + acc1));
+          if (valid) mel_row[m] = fminf(fmaxf(fmaf(lm, fm_a, fm_b), clip_lo), clip_hi);
+        }
+        __syncwarp();
+        continue;
       }
       if (lane == 0) {   // k = 512: X = conj(Z)
         const int sl = 16;
@@ -880,12 +979,16 @@ __global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> 
   }
 }
 
+// melp_total > 0 selects the dB-feature layout (padded float table + k0) instead of the CSR one.
 template <typename T>
-SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_mels, int mel_nnz) {
+SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_mels, int mel_nnz,
+                                        int melp_total = 0) {
+  const size_t mel = melp_total > 0
+      ? sizeof(float) * (size_t)round_up4(melp_total) + sizeof(int) * (size_t)round_up4(n_mels)
+      : sizeof(T) * (size_t)round_up4(mel_nnz) + sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
   return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
          sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win + WIN_TAB_PAD)) +
-         sizeof(float) * 2 * (size_t)round_up4(span_max) + sizeof(T) * (size_t)round_up4(mel_nnz) +
-         sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
+         sizeof(float) * 2 * (size_t)(round_up4(span_max) + 8) + mel;
 }
 
 // =============================================================================================

@@ -26,7 +26,7 @@ def load():
                                                            ctypes.c_int]
         lib.emu_stft_features.argtypes = ([ctypes.c_int] * 6 + [ctypes.c_double] * 2 +
                                           [ctypes.c_int, _lp, ctypes.c_int, _fp, _fp, _fp, _fp, _dp,
-                                           _dp, ctypes.c_int] + [ctypes.c_double] * 5 + [ctypes.c_int])
+                                           _dp, ctypes.c_int] + [ctypes.c_double] * 5 + [ctypes.c_int] * 2)
         lib.emu_mel_basis.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double] * 2 + [_dp]
         lib.emu_trim_bounds.argtypes = [_fp, ctypes.c_int, _lp, _lp, ctypes.c_double, ctypes.c_int, ctypes.c_int, _lp]
         _lib = lib
@@ -60,7 +60,8 @@ def griffin_lim(mags, angles, n_iter, prec=0, win=1102, hop=275, want_mse=False,
 
 
 def stft_features(wavs, prec=1, r=1, n_fft=2048, win=1102, hop=275, sr=22050, n_mels=80, fmin=0.,
-                  fmax=8000., normalize=None, power=1.0, grid_cap=3):
+                  fmax=8000., normalize=None, power=1.0, grid_cap=3, fast=False):
+    """fast=True requests only lin + mel dB, which selects the kernel's fused dB-feature mode."""
     nb = n_fft // 2 + 1
     so = np.concatenate([[0], np.cumsum([len(w) for w in wavs])]).astype(np.int64)
     wav = np.concatenate(wavs).astype(np.float32)
@@ -75,9 +76,10 @@ def stft_features(wavs, prec=1, r=1, n_fft=2048, win=1102, hop=275, sr=22050, n_
     consts = normalize if normalize is not None else (0., 0., 0., 0.)
     rc = _lib.emu_stft_features(n_fft, win, hop, prec, sr, n_mels, fmin, fmax, len(wavs),
                                 so.ctypes.data_as(_lp), r, wav.ctypes.data_as(_fp),
-                                spec.view(np.float32).ctypes.data_as(_fp), lin.ctypes.data_as(_fp),
-                                mel.ctypes.data_as(_fp), melraw.ctypes.data_as(_dp), mm.ctypes.data_as(_dp),
-                                int(normalize is not None), *consts, power, grid_cap)
+                                None if fast else spec.view(np.float32).ctypes.data_as(_fp), lin.ctypes.data_as(_fp),
+                                mel.ctypes.data_as(_fp), None if fast else melraw.ctypes.data_as(_dp),
+                                None if fast else mm.ctypes.data_as(_dp),
+                                int(normalize is not None), *consts, power, grid_cap, int(fast))
     assert rc == 0
     return [dict(spec=spec[ro[i]:ro[i + 1]], lin=lin[ro[i]:ro[i + 1]], mel=mel[ro[i]:ro[i + 1]],
                  melraw=melraw[ro[i]:ro[i + 1]], minmax=mm[i], T=Ts[i]) for i in range(len(wavs))]

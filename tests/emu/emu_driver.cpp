@@ -105,7 +105,7 @@ template <typename T, typename G, int W>
 int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, double fmax, int n_clips,
                  const long long* sample_off, int reduction, const float* wav, float* spec, float* lin,
                  float* mel, double* melraw, double* minmax, int normalize, double lin_ref,
-                 double lin_max, double mel_ref, double mel_max, double power, int grid_cap) {
+                 double lin_max, double mel_ref, double mel_max, double power, int grid_cap, int fast_mode) {
   FeatPlanHost H;
   std::string err;
   std::vector<long long> cs(n_clips), cl(n_clips);
@@ -115,10 +115,15 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   fill_tables<T>(win, tabs);
   MelCSR M;
   std::vector<T> mw;
+  MelPadded MP;
   if (n_mels > 0) {
     make_mel_csr(sr, n_fft, n_mels, fmin, fmax > 0 ? fmax : sr / 2.0, M);
     mw.assign(M.w.begin(), M.w.end());
+    make_mel_padded(M, n_mels, FEAT_PLANE_ELEMS, MP);
   }
+  // same selection rule as sstts.cu:run_features
+  const bool fast = fast_mode && MP.ok && n_fft == NFFT && lin && mel && !spec && !melraw && !minmax && power == 1.0;
+  if (fast_mode && !fast) { fprintf(stderr, "dB-feature mode does not apply to this request\n"); return -2; }
   std::vector<long long> mm(4 * (size_t)n_clips);
   FeatArgs<T> A;
   A.wav = wav; A.sample_off = H.sample_off.data(); A.sample_len = H.sample_len.data(); A.frame_off = H.frame_off.data();
@@ -131,10 +136,13 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   A.mel_ref_db = mel_ref; A.mel_range_db = fabs(mel_ref) + fabs(mel_max);
   A.mel_power = (float)power; A.normalize = normalize;
   A.win = win; A.hop = hop; A.span_max = H.span_max; A.n_fft = n_fft;
+  A.melp_w = MP.w.data(); A.melp_slots = fast ? MP.n_slots : 0; A.melp_total = fast ? MP.total : 0;
+  for (int j = 0; j < 4; ++j) { A.melp_len[j] = MP.len[j]; A.melp_woff[j] = MP.woff[j]; A.melp_mbase[j] = MP.mbase[j]; }
   if (minmax) for (size_t i = 0; i < mm.size(); ++i) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
-  const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max, n_mels, (int)mw.size());
+  const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max, n_mels, (int)mw.size(), A.melp_total);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
-  emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { stft_feature_kernel<T, G, W>(A); });
+  if (fast) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { stft_feature_kernel<T, G, W, FeatMode::kDbFeatures>(A); });
+  else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { stft_feature_kernel<T, G, W, FeatMode::kGeneric>(A); });
   if (minmax) for (size_t i = 0; i < mm.size(); ++i) {
     long long c = mm[i]; c = c >= 0 ? c : (c ^ 0x7fffffffffffffffLL);
     std::memcpy(&minmax[i], &c, 8);
@@ -178,10 +186,10 @@ int emu_griffin_lim(int win, int hop, int prec, int n_utts, const long long* fra
 int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels, double fmin, double fmax, int n_clips,
                       const long long* sample_off, int reduction, const float* wav, float* spec, float* lin,
                       float* mel, double* melraw, double* minmax, int normalize, double lin_ref,
-                      double lin_max, double mel_ref, double mel_max, double power, int grid_cap) {
+                      double lin_max, double mel_ref, double mel_max, double power, int grid_cap, int fast_mode) {
   const bool model = (n_fft == 2048 && win == 1102 && hop == 275);
   const bool stats = (n_fft == 1024 && win == 1024 && hop == 256);
-#define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap
+#define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap, fast_mode
   if (prec == 1) {
     if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
     if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);

@@ -104,6 +104,28 @@ def test_feature_pipeline(emu, prec, tol_lin):
         assert np.abs(r['melraw'][:r['T']] - mr).max() / np.abs(mr).max() < 1e-6
 
 
+@pytest.mark.parametrize('prec,tol_lin', [(1, 5e-7), (0, 2e-3)])
+@pytest.mark.parametrize('normalize', [(35.66, 100.0, 6.02, 99.89), None])
+def test_feature_pipeline_fused_db_mode(emu, prec, tol_lin, normalize):
+    """The fused dB-feature kernel mode (lin + mel dB only: the pre-calculation request) against the
+    oracle and against the generic mode; clips long enough for interior tiles (16-byte staging with
+    every misalignment) next to the short / reflecting ones."""
+    rng = np.random.default_rng(17)
+    lens = [1, 274, 275, 1500, 5003, 9001, 12345]
+    wavs = [speech_like_clip(max(n, 8), rng)[:n] for n in lens]
+    fast = emu.stft_features(wavs, prec=prec, r=5, normalize=normalize, fast=True)
+    slow = emu.stft_features(wavs, prec=prec, r=5, normalize=normalize)
+    for w, f, g in zip(wavs, fast, slow):
+        assert not np.isnan(f['lin']).any() and not np.isnan(f['mel']).any()
+        scale = 1.0 if normalize is not None else 135.0      # dB instead of (0, 1)
+        assert np.abs(f['lin'] - g['lin']).max() < 2e-6 * scale
+        assert np.abs(f['mel'] - g['mel']).max() < 2e-6 * scale
+        if normalize is not None:
+            mel_ref, lin_ref = ra.load_audio_from_wav(w, 22050, trim=False)
+            assert np.abs(f['lin'] - lin_ref.reshape(-1, 1025)).max() < tol_lin
+            assert np.abs(f['mel'] - mel_ref.reshape(-1, 80)).max() < 3e-6
+
+
 def test_decibel_statistics_geometry(emu):
     """datasets/statistics.py:31-51: n_fft 1024 / hop 256 / win 1024, fmax sr//2, embedded in the
     2048-point transform (every other bin)."""
