@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 _CHUNK_BYTES = 32 << 20
-_N_WORKERS = 4
+_N_WORKERS = 8
 _tls = threading.local()
 _executor = None
 _executor_lock = threading.Lock()

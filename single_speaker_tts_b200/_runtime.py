@@ -67,11 +67,16 @@ class _Plan:
 
 
 class _PlanCache:
-    """Small thread-safe LRU of native plans keyed by geometry + batch shape + device."""
+    """Small thread-safe LRU of native plans keyed by geometry + batch shape + device.
 
-    def __init__(self, capacity=8):
+    Destroying a plan frees device memory (``cudaFree`` waits for the device), so evicted plans are
+    parked and only released by :meth:`reap`, which the batch entry points call after their final
+    synchronisation -- an eviction in the middle of a sub-batch pipeline would stall it."""
+
+    def __init__(self, capacity=64):
         self._cap = capacity
         self._d = collections.OrderedDict()
+        self._dead = []
         self._lock = threading.Lock()
 
     def get(self, key, factory):
@@ -84,8 +89,13 @@ class _PlanCache:
         with self._lock:
             self._d[key] = plan
             while len(self._d) > self._cap:
-                self._d.popitem(last=False)
+                self._dead.append(self._d.popitem(last=False)[1])
         return plan
+
+    def reap(self):
+        with self._lock:
+            dead, self._dead = self._dead, []
+        del dead
 
 
 _gl_plans = _PlanCache()
@@ -101,31 +111,40 @@ def _offsets(counts):
 # ----------------------------------------------------------------------------------------------
 # Griffin-Lim
 # ----------------------------------------------------------------------------------------------
-# Batches above this many frames are split into sub-batches whose uploads overlap the previous
-# sub-batch's iterations (copy stream + events); results do not depend on the split.
-_GL_CHUNK_FRAMES = 24000
-_copy_streams = threading.local()
+# Large batches are split into equal sub-batches whose packing + upload overlaps the previous
+# sub-batch's iterations (copy streams + events); results do not depend on the split.  Packing into
+# pinned memory (~25-35 GB/s with the staging threads) is faster than the device iterates, so only the
+# first sub-batch's upload is exposed; sub-batches alternate between two compute streams so that the
+# tail of one launch (the last, partly filled wave of tiles) is filled by the next sub-batch's CTAs.
+# tools/e2e_probe.py measures the trade-off (more sub-batches: shorter exposed upload, more launches).
+_GL_CHUNK_FRAMES = 10000
+_GL_CHUNK_GROWTH = 1
+_aux_streams = threading.local()
 
 
-def _copy_stream(dev):
-    d = getattr(_copy_streams, 'd', None)
+def _aux_stream(dev, name):
+    d = getattr(_aux_streams, 'd', None)
     if d is None:
-        d = _copy_streams.d = {}
-    if dev.index not in d:
-        d[dev.index] = torch.cuda.Stream(device=dev)
-    return d[dev.index]
+        d = _aux_streams.d = {}
+    if (dev.index, name) not in d:
+        d[(dev.index, name)] = torch.cuda.Stream(device=dev)
+    return d[(dev.index, name)]
 
 
-def _split_by_frames(frames, limit):
-    """Contiguous index ranges of roughly `limit` frames each."""
-    ranges, i0, acc = [], 0, 0
+def _split_by_frames(frames, first, growth=1):
+    """Contiguous index ranges of roughly first, first * growth, first * growth ** 2, ... frames;
+    a short remainder is merged into the last range."""
+    ranges, i0, acc, limit = [], 0, 0, first
     for i, t in enumerate(frames):
         acc += t
         if acc >= limit:
             ranges.append((i0, i + 1))
-            i0, acc = i + 1, 0
+            i0, acc, limit = i + 1, 0, limit * growth
     if i0 < len(frames):
-        ranges.append((i0, len(frames)))
+        if ranges and acc * 4 < limit // max(growth, 1):
+            ranges[-1] = (ranges[-1][0], len(frames))
+        else:
+            ranges.append((i0, len(frames)))
     return ranges
 
 
@@ -175,7 +194,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
     cfg = _make_config(n_fft, win_length, hop_length, precision)
     i64p = ctypes.POINTER(ctypes.c_int64)
-    ranges = _split_by_frames(frames, _GL_CHUNK_FRAMES)
+    ranges = _split_by_frames(frames, _GL_CHUNK_FRAMES, _GL_CHUNK_GROWTH)
     frame_base = _offsets(frames)
 
     def get_plan(i0, i1):
@@ -193,7 +212,10 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
 
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
-        copy = _copy_stream(dev) if len(ranges) > 1 else main
+        piped = len(ranges) > 1
+        copy = _aux_stream(dev, 'h2d') if piped else main     # uploads
+        back = _aux_stream(dev, 'd2h') if piped else main     # result downloads (other DMA direction)
+        compute = [main, _aux_stream(dev, 'gl1')] if piped else [main]
 
         def upload(k):
             """Pack + H2D of sub-batch k on the copy stream; returns device tensors and an event."""
@@ -211,38 +233,59 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
             return mag_dev, ph_dev, ev
 
         flag_dev = torch.zeros(1, dtype=torch.int32, device=dev) if denormalize is not None else None
+        if piped and flag_dev is not None:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            compute[1].wait_event(ready)
+            flag_dev.record_stream(compute[1])
         outs = []
         nxt = upload(0)
         for k, (i0, i1) in enumerate(ranges):
             mag_dev, phase_dev, ev = nxt
             plan, fo = get_plan(i0, i1)
             tf = int(fo[-1])
-            main.wait_event(ev)
-            # tensors allocated on the copy stream are consumed on the compute stream
-            mag_dev.record_stream(main)
-            if phase_dev is not None:
-                phase_dev.record_stream(main)
-            if denormalize is not None:
-                ref_db, max_db, power = [float(v) for v in denormalize]
-                _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), tf * n_bins, ref_db, max_db, power,
-                                                           _ptr(mag_dev), _ptr(flag_dev), _stream_ptr()))
-            if phase_dev is None:
-                phase_dev = torch.empty((tf, n_bins, 2), dtype=torch.float32, device=dev)
-                _lib.check(lib.sstts_random_phase_at(ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
-                                                     int(frame_base[i0]) * n_bins, tf * n_bins,
-                                                     _ptr(phase_dev), _stream_ptr()))
-            ts = int(lib.sstts_gl_total_samples(plan.handle))
-            so = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(i1 - i0 + 1,)).copy()
-            ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan.handle)), dtype=torch.uint8, device=dev)
-            wav_dev = torch.empty(max(ts, 1), dtype=torch.float32, device=dev)
-            mse_dev = torch.zeros(tf, dtype=torch.float64, device=dev) if return_mse else None
-            _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
-                                             _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
-            outs.append((_hostio.download(wav_dev), _hostio.download(mse_dev) if return_mse else None, so, fo))
+            comp = compute[k % len(compute)]
+            with torch.cuda.stream(comp):
+                comp.wait_event(ev)
+                # tensors allocated on the copy stream are consumed on the compute stream
+                mag_dev.record_stream(comp)
+                if phase_dev is not None:
+                    phase_dev.record_stream(comp)
+                if denormalize is not None:
+                    ref_db, max_db, power = [float(v) for v in denormalize]
+                    _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), tf * n_bins, ref_db, max_db, power,
+                                                               _ptr(mag_dev), _ptr(flag_dev), _stream_ptr()))
+                if phase_dev is None:
+                    phase_dev = torch.empty((tf, n_bins, 2), dtype=torch.float32, device=dev)
+                    _lib.check(lib.sstts_random_phase_at(ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                                         int(frame_base[i0]) * n_bins, tf * n_bins,
+                                                         _ptr(phase_dev), _stream_ptr()))
+                ts = int(lib.sstts_gl_total_samples(plan.handle))
+                so = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(i1 - i0 + 1,)).copy()
+                ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan.handle)), dtype=torch.uint8, device=dev)
+                wav_dev = torch.empty(max(ts, 1), dtype=torch.float32, device=dev)
+                mse_dev = torch.zeros(tf, dtype=torch.float64, device=dev) if return_mse else None
+                _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
+                                                 _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
+                # results go back on their own stream so that the next iterations start at once
+                if piped:
+                    done = torch.cuda.Event()
+                    done.record(comp)
+                    back.wait_event(done)
+                    wav_dev.record_stream(back)
+                    if mse_dev is not None:
+                        mse_dev.record_stream(back)
+            with torch.cuda.stream(back):
+                outs.append((_hostio.download(wav_dev), _hostio.download(mse_dev) if return_mse else None, so, fo))
             if k + 1 < len(ranges):
                 nxt = upload(k + 1)          # host packing + H2D overlap the iterations just enqueued
+        if piped:
+            compute[1].synchronize()
         flag = _hostio.download(flag_dev) if flag_dev is not None else None
         main.synchronize()
+        if piped:
+            back.synchronize()
+    _gl_plans.reap()
     if flag is not None and int(flag[0]) != 0:
         # same error as the reference's decibel_to_magnitude (audio/conversion.py:47-49)
         raise AssertionError('"conversion.decibel_to_magnitude" was asked to convert a dB value '
@@ -286,7 +329,8 @@ class FeatureBatch:
 def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None, n_mels=0, fmin=0.0,
                         fmax=None, reduction=1, want_spec=False, want_lin=False, want_mel=False,
                         want_mel_raw=False, want_minmax=False, normalize=None, power=1.0,
-                        precision='f64', device=None, keep_on_device=False, trim=None, force_generic=False):
+                        precision='f64', device=None, keep_on_device=False, trim=None, force_generic=False,
+                        _streams=None, _slot=0):
     """Batched STFT -> |.| -> linear / mel -> dB -> (0,1) pipeline on the GPU.
 
     normalize: None (raw dB) or (lin_ref_db, lin_max_db, mel_ref_db, mel_max_db) as in
@@ -297,6 +341,8 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     on the trimmed part of the same upload and ``result.trim_bounds`` holds (start, end) per clip.
     force_generic: run the kernel's generic mode even where the fused dB-feature mode applies (lin +
     mel dB only, n_fft 2048, power 1) -- for validation; the two agree to float32 rounding.
+    _streams / _slot: used by :func:`stft_features_parts` -- (upload, download) side streams; the call
+    then returns without synchronising and the caller synchronises both streams.
     """
     lib = _lib.load()
     dev = require_cuda(device)
@@ -324,7 +370,16 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     clip_len = np.asarray(lens, dtype=np.int64)
     trim_bounds = None
     with torch.cuda.device(dev):
-        wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav')
+        main = torch.cuda.current_stream()
+        if _streams is not None:
+            with torch.cuda.stream(_streams[0]):
+                wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav%d' % (_slot & 1))
+                up = torch.cuda.Event()
+                up.record(_streams[0])
+            main.wait_event(up)
+            wav_dev.record_stream(main)
+        else:
+            wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav')
         if trim is not None:
             top_db, t_frame, t_hop = trim
             start_dev = torch.from_numpy(clip_start).to(dev)
@@ -381,10 +436,49 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             res.lin_db, res.mel_db, res.mel_raw, res.minmax = lin_dev, mel_dev, raw_dev, mm_dev
             return res
 
-        res.spec = _hostio.download(spec_dev).view(np.complex64).reshape(rows, n_bins) if want_spec else None
-        res.lin_db = _hostio.download(lin_dev) if want_lin else None
-        res.mel_db = _hostio.download(mel_dev) if want_mel else None
-        res.mel_raw = _hostio.download(raw_dev) if want_mel_raw else None
-        res.minmax = _hostio.download(mm_dev) if want_minmax else None
-        torch.cuda.current_stream().synchronize()
+        back = main
+        if _streams is not None:
+            back = _streams[1]
+            done = torch.cuda.Event()
+            done.record(main)
+            back.wait_event(done)
+            for t in (spec_dev, lin_dev, mel_dev, raw_dev, mm_dev):
+                if t is not None:
+                    t.record_stream(back)
+        with torch.cuda.stream(back):
+            res.spec = _hostio.download(spec_dev).view(np.complex64).reshape(rows, n_bins) if want_spec else None
+            res.lin_db = _hostio.download(lin_dev) if want_lin else None
+            res.mel_db = _hostio.download(mel_dev) if want_mel else None
+            res.mel_raw = _hostio.download(raw_dev) if want_mel_raw else None
+            res.minmax = _hostio.download(mm_dev) if want_minmax else None
+        if _streams is None:
+            main.synchronize()
+    if _streams is None:
+        _feat_plans.reap()
     return res
+
+
+# Sub-batches of about this many samples: while one is being transformed, the next one is packed
+# and uploaded and the previous one's features travel back (H2D and D2H use different DMA engines).
+_FEAT_CHUNK_SAMPLES = 3 << 20
+
+
+def stft_features_parts(wavs, *args, **kwargs):
+    """:func:`stft_features_batch` for large batches as a pipeline of sub-batches: returns a list of
+    ``(i0, i1, FeatureBatch)`` covering ``wavs[i0:i1]``.  Per-clip results are identical to one big
+    call (clips are independent); the output (4.4 KB per frame) dominates the PCIe traffic, so the
+    gain is the overlap of uploads, kernels and downloads."""
+    wavs = list(wavs)
+    dev = require_cuda(kwargs.get('device'))
+    ranges = _split_by_frames([int(w.shape[0]) for w in wavs], _FEAT_CHUNK_SAMPLES)
+    if len(ranges) < 2 or kwargs.get('keep_on_device'):
+        return [(0, len(wavs), stft_features_batch(wavs, *args, **kwargs))]
+    with torch.cuda.device(dev):
+        streams = (_aux_stream(dev, 'h2d'), _aux_stream(dev, 'd2h'))
+        parts = []
+        for k, (i0, i1) in enumerate(ranges):
+            parts.append((i0, i1, stft_features_batch(wavs[i0:i1], *args, _streams=streams, _slot=k, **kwargs)))
+        torch.cuda.current_stream().synchronize()
+        streams[1].synchronize()
+    _feat_plans.reap()
+    return parts

@@ -39,16 +39,17 @@ def features_batch(wavs, n_fft, hop_length, win_length, sampling_rate, n_mels, f
     ``(ceil(T/r), r * n_mels)`` and ``(ceil(T/r), r * (1 + n_fft/2))``.
     ``trim=(top_db, frame_length, hop_length)`` runs the ``librosa.effects.trim`` step of
     datasets/lj_speech.py:119 on the device first."""
-    res = _runtime.stft_features_batch(list(wavs), n_fft, hop_length, win_length,
-                                       sampling_rate=sampling_rate, n_mels=n_mels, fmin=fmin,
-                                       fmax=fmax, reduction=reduction, want_lin=True, want_mel=True,
-                                       normalize=(linear_ref_db, linear_mag_max_db, mel_mag_ref_db,
-                                                  mel_mag_max_db),
-                                       precision=precision, trim=trim)
+    parts = _runtime.stft_features_parts(list(wavs), n_fft, hop_length, win_length,
+                                         sampling_rate=sampling_rate, n_mels=n_mels, fmin=fmin,
+                                         fmax=fmax, reduction=reduction, want_lin=True, want_mel=True,
+                                         normalize=(linear_ref_db, linear_mag_max_db, mel_mag_ref_db,
+                                                    mel_mag_max_db),
+                                         precision=precision, trim=trim)
     out = []
     n_bins = 1 + n_fft // 2
-    for i in range(res.n_clips):
-        mel = res.rows(res.mel_db, i, padded=True).reshape((-1, n_mels * reduction))
-        lin = res.rows(res.lin_db, i, padded=True).reshape((-1, n_bins * reduction))
-        out.append((mel, lin))
+    for _, _, res in parts:
+        for i in range(res.n_clips):
+            mel = res.rows(res.mel_db, i, padded=True).reshape((-1, n_mels * reduction))
+            lin = res.rows(res.lin_db, i, padded=True).reshape((-1, n_bins * reduction))
+            out.append((mel, lin))
     return out

@@ -12,7 +12,7 @@ import torch
 
 from oracle import librosa_compat as lc
 from oracle import reference_audio as ra
-from single_speaker_tts_b200 import _lib
+from single_speaker_tts_b200 import _lib, _runtime
 from single_speaker_tts_b200.audio import features, synthesis
 from single_speaker_tts_b200.datasets import statistics
 from single_speaker_tts_b200.datasets.dataset_helper import LJSpeechDatasetHelper
@@ -119,8 +119,9 @@ def test_griffin_lim_sub_batch_pipeline_is_invisible(monkeypatch):
     mags, angs = _case([40, 9, 100, 17, 64, 3])
     whole = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 4, angles=angs)
     whole_seeded, mse_whole = _runtime.griffin_lim_batch(mags, WIN, HOP, NFFT, 4, seed=99, return_mse=True)
-    monkeypatch.setattr(_runtime, '_GL_CHUNK_FRAMES', 50)
-    assert len(_runtime._split_by_frames([m.shape[1] for m in mags], 50)) > 2
+    monkeypatch.setattr(_runtime, '_GL_CHUNK_FRAMES', 30)
+    monkeypatch.setattr(_runtime, '_GL_CHUNK_GROWTH', 2)
+    assert len(_runtime._split_by_frames([m.shape[1] for m in mags], 30, 2)) >= 3
     split = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 4, angles=angs)
     split_seeded, mse_split = _runtime.griffin_lim_batch(mags, WIN, HOP, NFFT, 4, seed=99, return_mse=True)
     for a, b, c, d in zip(whole, split, whole_seeded, split_seeded):
@@ -207,6 +208,32 @@ def test_features_public_functions_vs_oracle():
     assert np.abs(st - ra.decibel_statistics(x, 22050)).max() < 1e-3
     with pytest.raises(ValueError):
         features.linear_scale_spectrogram(np.zeros((2, 100), np.float32), NFFT, HOP, WIN)
+
+
+def test_features_sub_batch_pipeline_and_fused_mode_are_invisible(monkeypatch):
+    """features_batch runs large batches as a pipeline of sub-batches on side streams and picks the
+    fused dB-feature kernel mode: per-clip results must equal the single-batch call bit for bit, and
+    the fused mode must agree with the generic kernel mode to float32 rounding."""
+    rng = np.random.default_rng(21)
+    clips = [speech_like_clip(int(n), rng) for n in (9000, 300, 22050, 5000, 14000, 275, 31000)]
+    consts = (35.66, 100.0, 6.02, 99.89)
+    whole = features.features_batch(clips, NFFT, HOP, WIN, 22050, 80, 0, 8000, *consts, reduction=5)
+    monkeypatch.setattr(_runtime, '_FEAT_CHUNK_SAMPLES', 10000)
+    assert len(_runtime._split_by_frames([len(c) for c in clips], 10000)) >= 3
+    split = features.features_batch(clips, NFFT, HOP, WIN, 22050, 80, 0, 8000, *consts, reduction=5)
+    for (m0, l0), (m1, l1) in zip(whole, split):
+        assert np.array_equal(m0, m1) and np.array_equal(l0, l1)
+    for prec in ('f64', 'f32'):
+        kw = dict(sampling_rate=22050, n_mels=80, fmin=0, fmax=8000, reduction=5, want_lin=True, want_mel=True,
+                  normalize=consts, precision=prec)
+        fused = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, **kw)
+        generic = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, force_generic=True, **kw)
+        assert np.abs(fused.lin_db - generic.lin_db).max() < 2e-6
+        assert np.abs(fused.mel_db - generic.mel_db).max() < 2e-6
+        raw_f = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, **dict(kw, normalize=None))
+        raw_g = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, force_generic=True, **dict(kw, normalize=None))
+        assert np.abs(raw_f.lin_db - raw_g.lin_db).max() < 3e-4      # dB, i.e. 2e-6 of the 135 dB range
+        assert np.abs(raw_f.mel_db - raw_g.mel_db).max() < 3e-4
 
 
 def test_features_f32_fast_mode_error_is_bounded():

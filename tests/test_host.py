@@ -146,3 +146,18 @@ def test_bench_reference_arm_line_shape():
     d = json.loads(line)
     assert d['impl'] == 'reference' and d['unit'] == 'audio-s/s' and d['value'] > 0
     assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_gl_sub_batch_split_covers_every_utterance_once():
+    """Host-side pipeline plan of griffin_lim_batch: contiguous ranges, geometric growth, remainder merged."""
+    from single_speaker_tts_b200._runtime import _split_by_frames
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        frames = rng.integers(1, 900, size=int(rng.integers(1, 300))).tolist()
+        for first, growth in ((6000, 3), (50, 1), (30, 2), (10 ** 9, 3)):
+            ranges = _split_by_frames(frames, first, growth)
+            assert ranges[0][0] == 0 and ranges[-1][1] == len(frames)
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            assert all(i1 > i0 for i0, i1 in ranges)
+    sizes = [400 * (i1 - i0) for i0, i1 in _split_by_frames([400] * 300, 6000, 3)]
+    assert sizes[0] == 6000 and sizes[1] == 18000 and sizes[2] == 54000 and sum(sizes) == 120000
