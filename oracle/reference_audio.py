@@ -193,6 +193,68 @@ def load_audio_from_wav(wav, sr, constants=LJSpeechConstants, params=ModelParams
     return np.array(mel_mag_db).astype(np.float32), np.array(linear_mag_db).astype(np.float32)
 
 
+class BlizzardNancyConstants:      # datasets/blizzard_nancy.py:20-29
+    mel_mag_ref_db = 9.55
+    mel_mag_max_db = 100.0
+    linear_ref_db = 36.50
+    linear_mag_max_db = 100.0
+
+
+class CMUConstants:                # datasets/cmu_slt.py:19-28
+    mel_mag_ref_db = 9.33
+    mel_mag_max_db = 100.0
+    linear_ref_db = 36.50
+    linear_mag_max_db = 100.0
+
+
+class PAVOQUEConstants:            # datasets/pavoque.py:20-32
+    mel_mag_ref_db = 12.63
+    mel_mag_max_db = 100.0
+    linear_ref_db = 24
+    linear_mag_max_db = 100.0
+    raw_silence_db = -15.0
+
+
+def silence_interval_from_spectrogram(mag_spec_db, threshold_db, ref=np.max):
+    """audio/effects.py:218-232."""
+    ref_trim_spec_db = ref(mag_spec_db, axis=0)
+    non_silent = np.array(ref_trim_spec_db > threshold_db, dtype=np.int32)
+    nonzero = np.flatnonzero(non_silent)
+    if len(nonzero) == 0:
+        return None
+    return np.min(nonzero), np.max(nonzero)
+
+
+def pavoque_load_audio_from_wav(wav, sr, constants=PAVOQUEConstants, params=ModelParams):
+    """datasets/pavoque.py:104-160 after the file decode (:112)."""
+    win_len = ms_to_samples(params.win_len, params.sampling_rate)
+    hop_len = ms_to_samples(params.win_hop, params.sampling_rate)
+    linear_spec = linear_scale_spectrogram(wav, params.n_fft, hop_len, win_len).T
+    linear_spec = np.array(linear_spec)
+    linear_spec[:, 0:8] = 0                                                          # :119
+    linear_mag_db = magnitude_to_decibel(np.abs(linear_spec))
+    linear_mag_db = normalize_decibel(linear_mag_db, constants.linear_ref_db, constants.linear_mag_max_db)
+    trim_start, trim_end = silence_interval_from_spectrogram(linear_mag_db, constants.raw_silence_db, np.max)
+    mel_spec = mel_scale_spectrogram(wav, params.n_fft, sr, params.n_mels, params.mel_fmin,
+                                     params.mel_fmax, hop_len, win_len, 1).T
+    mel_mag_db = magnitude_to_decibel(np.abs(mel_spec))
+    mel_mag_db = normalize_decibel(mel_mag_db, constants.mel_mag_ref_db, constants.mel_mag_max_db)
+    linear_mag_db = linear_mag_db[trim_start:trim_end, :]
+    mel_mag_db = mel_mag_db[trim_start:trim_end, :]
+    if params.reduction > 1:
+        mel_mag_db, linear_mag_db = apply_reduction_padding(mel_mag_db, linear_mag_db, params.reduction)
+    return np.array(mel_mag_db).astype(np.float32), np.array(linear_mag_db).astype(np.float32)
+
+
+def reconstruction_error(wav, sampling_rate, n_iters, angles=None):
+    """Loop body of collect_reconstruction_error, datasets/statistics.py:156-181."""
+    win = ms_to_samples(50.0, sampling_rate)
+    hop = ms_to_samples(12.5, sampling_rate)
+    mag = np.abs(linear_scale_spectrogram(wav, 2048, hop, win))
+    _, mse = griffin_lim_v2(mag, win, hop, 2048, n_iters, angles=angles, batched_fft=True)
+    return mse
+
+
 # ----------------------------------------------------------------------------------------------
 # tacotron/inference.py glue before Griffin-Lim
 # ----------------------------------------------------------------------------------------------

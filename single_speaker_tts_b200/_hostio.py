@@ -8,8 +8,8 @@ of waveform come out per 256-utterance Griffin-Lim batch.  This module keeps tha
 * pinned staging buffers are pooled per thread and reused (``cudaHostAlloc`` of hundreds of MB
   costs more than the Griffin-Lim kernels);
 * packing into the staging buffer is done by a few worker threads (``np.copyto`` releases the
-  GIL) in chunks, and every chunk's H2D copy is issued as soon as it is packed, so packing and
-  DMA overlap;
+  GIL) in chunks -- one task per worker and chunk, each a contiguous run of arrays -- and every
+  chunk's H2D copy is issued as soon as it is packed, so packing and DMA overlap;
 * results are copied straight into pinned blocks of torch's caching host allocator and handed to
   the caller as numpy views of them (no second host copy).
 """
@@ -63,6 +63,39 @@ def _thread_buffers():
     return _tls
 
 
+def _copy_group(pairs):
+    for dst, src in pairs:
+        np.copyto(dst, src, 'unsafe')
+
+
+def _pack_and_copy(views, srcs, sizes, stage, out, itemsize_row):
+    """Pack ``srcs[k]`` into ``views[k]`` (slices of the pinned ``stage``) with the worker threads and
+    issue the H2D copy of every ~_CHUNK_BYTES piece as soon as it is packed.  Every worker gets a
+    contiguous run of arrays of about equal bytes -- one task per worker and chunk, not one per
+    array (a task hand-over costs as much as copying ~100 KB)."""
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    per_chunk = max(1, _CHUNK_BYTES // itemsize_row)
+    ex = _pool()
+    n = len(srcs)
+    i = 0
+    while i < n:
+        j = i
+        while j < n and (starts[j + 1] - starts[i] <= per_chunk or j == i):
+            j += 1
+        total = starts[j] - starts[i]
+        target = max(1, -(-int(total) // _N_WORKERS))
+        futs, g0, acc = [], i, 0
+        for k in range(i, j):
+            acc += sizes[k]
+            if acc >= target or k == j - 1:
+                futs.append(ex.submit(_copy_group, [(views[q], srcs[q]) for q in range(g0, k + 1)]))
+                g0, acc = k + 1, 0
+        for f in futs:
+            f.result()
+        out[starts[i]:starts[j]].copy_(stage[starts[i]:starts[j]], non_blocking=True)
+        i = j
+
+
 def upload_rows(blocks, width, dtype, device, slot='a'):
     """Stack 2-D host blocks (rows_i, width) -- any layout / float dtype -- into one device tensor
     (sum rows, width) of ``dtype``.  Packing and H2D are pipelined chunk by chunk."""
@@ -76,21 +109,9 @@ def upload_rows(blocks, width, dtype, device, slot='a'):
     pb = tl.up.setdefault(slot, _PinnedBuffer())
     stage = pb.get(total * width * itemsize)[:total * width * itemsize].view(dtype).view(total, width)
     stage_np = stage.numpy()
-    # chunk boundaries on block boundaries, ~_CHUNK_BYTES each
-    rows_per_chunk = max(1, _CHUNK_BYTES // (width * itemsize))
     starts = np.concatenate([[0], np.cumsum(rows)])
-    ex = _pool()
-    i = 0
-    while i < len(blocks):
-        j = i
-        while j < len(blocks) and (starts[j + 1] - starts[i] <= rows_per_chunk or j == i):
-            j += 1
-        futs = [ex.submit(np.copyto, stage_np[starts[k]:starts[k + 1]], blocks[k], 'unsafe')
-                for k in range(i, j)]
-        for f in futs:
-            f.result()
-        out[starts[i]:starts[j]].copy_(stage[starts[i]:starts[j]], non_blocking=True)
-        i = j
+    views = [stage_np[starts[k]:starts[k + 1]] for k in range(len(blocks))]
+    _pack_and_copy(views, blocks, rows, stage, out, width * itemsize)
     pb.mark()
     return out
 
@@ -108,19 +129,8 @@ def upload_flat(arrays, dtype, device, slot='w'):
     stage = pb.get(total * itemsize)[:total * itemsize].view(dtype)
     stage_np = stage.numpy()
     starts = np.concatenate([[0], np.cumsum(lens)])
-    per_chunk = max(1, _CHUNK_BYTES // itemsize)
-    ex = _pool()
-    i = 0
-    while i < len(arrays):
-        j = i
-        while j < len(arrays) and (starts[j + 1] - starts[i] <= per_chunk or j == i):
-            j += 1
-        futs = [ex.submit(np.copyto, stage_np[starts[k]:starts[k + 1]], arrays[k], 'unsafe')
-                for k in range(i, j)]
-        for f in futs:
-            f.result()
-        out[starts[i]:starts[j]].copy_(stage[starts[i]:starts[j]], non_blocking=True)
-        i = j
+    views = [stage_np[starts[k]:starts[k + 1]] for k in range(len(arrays))]
+    _pack_and_copy(views, arrays, lens, stage, out, itemsize)
     pb.mark()
     return out
 

@@ -460,7 +460,7 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
 
 # Sub-batches of about this many samples: while one is being transformed, the next one is packed
 # and uploaded and the previous one's features travel back (H2D and D2H use different DMA engines).
-_FEAT_CHUNK_SAMPLES = 3 << 20
+_FEAT_CHUNK_SAMPLES = 6 << 20
 
 
 def stft_features_parts(wavs, *args, **kwargs):

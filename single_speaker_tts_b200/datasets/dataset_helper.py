@@ -1,4 +1,5 @@
-"""Audio part of ``datasets/dataset_helper.py`` and ``datasets/lj_speech.py`` of the reference.
+"""Audio part of ``datasets/dataset_helper.py`` and the four corpus loaders of the reference
+(``datasets/lj_speech.py``, ``blizzard_nancy.py``, ``cmu_slt.py``, ``pavoque.py``).
 
 Only the feature side is restated (``load_audio``, ``apply_reduction_padding``,
 ``pre_compute_features``); the text side (vocabulary, sentence ids) is host string processing that
@@ -77,3 +78,69 @@ class LJSpeechDatasetHelper(DatasetHelper):
     mel_mag_max_db = 99.89
     linear_ref_db = 35.66
     linear_mag_max_db = 100.0
+
+
+class BlizzardNancyDatasetHelper(DatasetHelper):
+    """dB constants of reference datasets/blizzard_nancy.py:20-29 (same recipe as LJSpeech, :88-138)."""
+    mel_mag_ref_db = 9.55
+    mel_mag_max_db = 100.0
+    linear_ref_db = 36.50
+    linear_mag_max_db = 100.0
+
+
+class CMUDatasetHelper(DatasetHelper):
+    """dB constants of reference datasets/cmu_slt.py:19-28 (same recipe as LJSpeech, :87-137)."""
+    mel_mag_ref_db = 9.33
+    mel_mag_max_db = 100.0
+    linear_ref_db = 36.50
+    linear_mag_max_db = 100.0
+
+
+def silence_interval_from_spectrogram(mag_spec_db, threshold_db, ref=np.max):
+    """reference audio/effects.py:218-232, restated as written (``ref`` reduces over axis 0)."""
+    ref_trim_spec_db = ref(mag_spec_db, axis=0)
+    nonzero = np.flatnonzero(np.array(ref_trim_spec_db > threshold_db, dtype=np.int32))
+    if len(nonzero) == 0:
+        return None
+    return np.min(nonzero), np.max(nonzero)
+
+
+class PAVOQUEDatasetHelper(DatasetHelper):
+    """reference datasets/pavoque.py:20-32,104-160: no waveform trimming; the first 8 linear bins are
+    zeroed (``linear_spec[:, 0:8] = 0`` -> the -100 dB floor), and rows are cut with
+    ``silence_interval_from_spectrogram`` of the normalised linear spectrogram before the reduction
+    padding.  The STFT / dB / mel work is the same device batch as for the other corpora; the
+    corpus-specific slicing is host glue on the returned arrays."""
+    mel_mag_ref_db = 12.63
+    mel_mag_max_db = 100.0
+    linear_ref_db = 24
+    linear_mag_max_db = 100.0
+    raw_silence_db = -15.0
+
+    @classmethod
+    def features_from_wavs(cls, wavs, sampling_rate=None, trim_silence=True, precision='f64'):
+        sr = sampling_rate or model_params.sampling_rate
+        win_len = ms_to_samples(model_params.win_len, model_params.sampling_rate)
+        hop_len = ms_to_samples(model_params.win_hop, model_params.sampling_rate)
+        n_bins = 1 + model_params.n_fft // 2
+        feats = features_batch(wavs, model_params.n_fft, hop_len, win_len, sr, model_params.n_mels,
+                               model_params.mel_fmin, model_params.mel_fmax, cls.linear_ref_db,
+                               cls.linear_mag_max_db, cls.mel_mag_ref_db, cls.mel_mag_max_db,
+                               reduction=1, precision=precision, trim=None)
+        # normalised value of a zeroed bin: magnitude_to_decibel(0) = -100 dB (audio/conversion.py:29)
+        floor = np.float32(np.clip(1.0 + (np.float32(-100.0) - cls.linear_ref_db) /
+                                   (abs(cls.linear_ref_db) + abs(cls.linear_mag_max_db)), 0.0, 1.0))
+        out = []
+        for mel, lin in feats:
+            lin = lin.reshape(-1, n_bins).copy()
+            mel = mel.reshape(-1, model_params.n_mels)
+            lin[:, 0:8] = floor
+            interval = silence_interval_from_spectrogram(lin, cls.raw_silence_db, np.max)
+            if interval is None:
+                raise TypeError('cannot unpack non-iterable NoneType object')   # as the reference (:131)
+            trim_start, trim_end = interval
+            lin, mel = lin[trim_start:trim_end, :], mel[trim_start:trim_end, :]
+            if model_params.reduction > 1:
+                mel, lin = DatasetHelper.apply_reduction_padding(mel, lin, model_params.reduction)
+            out.append((np.array(mel).astype(np.float32), np.array(lin).astype(np.float32)))
+        return out

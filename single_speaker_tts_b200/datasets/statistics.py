@@ -66,3 +66,35 @@ def collect_decibel_statistics(path_listing, batch_clips=512, precision='f64'):
         if wavs:
             rows.append(decibel_statistics_batch(wavs, sr, precision=precision))
     return reduce_decibel_statistics(np.concatenate(rows, axis=0))
+
+
+def reconstruction_errors_from_wavs(wavs, sampling_rate, n_iters, seed=None):
+    """Per-clip Griffin-Lim reconstruction MSE (the loop body of reference
+    datasets/statistics.py:156-181) for decoded clips, batched: |STFT| (n_fft 2048, 50 ms / 12.5 ms
+    window) on the feature kernel, then ``n_iters`` Griffin-Lim iterations with the fused MSE of
+    audio/synthesis.py:112.  ``seed`` keys the device phase generator (None: fresh random)."""
+    from ..audio.conversion import ms_to_samples
+    n_fft = 2048
+    win = ms_to_samples(50.0, sampling_rate)
+    hop = ms_to_samples(12.5, sampling_rate)
+    wavs = [np.asarray(w) for w in wavs]
+    res = _runtime.stft_features_batch(wavs, n_fft, hop, win, want_spec=True)
+    mags = [np.abs(res.rows(res.spec, i)).T for i in range(res.n_clips)]
+    _, mses = _runtime.griffin_lim_batch(mags, win, hop, n_fft, n_iters, seed=seed, return_mse=True)
+    return mses
+
+
+def collect_reconstruction_error(path_listing, n_iters, batch_clips=64, seed=None):
+    """reference datasets/statistics.py:146-187: mean Griffin-Lim spectrogram MSE over a file list."""
+    print("Collecting reconstruction statistics for {} files ...".format(len(path_listing)))
+    mse_errors = []
+    for s in range(0, len(path_listing), batch_clips):
+        by_rate = {}
+        for path in path_listing[s:s + batch_clips]:
+            wav, sr = load_wav(path)
+            by_rate.setdefault(sr, []).append(wav)
+        for sr, wavs in by_rate.items():
+            mse_errors.extend(reconstruction_errors_from_wavs(wavs, sr, n_iters, seed=seed))
+    total_mse = sum(mse_errors) / len(mse_errors)
+    print('Dataset MSE with {} iterations: {}'.format(n_iters, total_mse))
+    return total_mse

@@ -15,7 +15,8 @@ from oracle import reference_audio as ra
 from single_speaker_tts_b200 import _lib, _runtime
 from single_speaker_tts_b200.audio import features, synthesis
 from single_speaker_tts_b200.datasets import statistics
-from single_speaker_tts_b200.datasets.dataset_helper import LJSpeechDatasetHelper
+from single_speaker_tts_b200.datasets.dataset_helper import (BlizzardNancyDatasetHelper, CMUDatasetHelper,
+                                                            LJSpeechDatasetHelper, PAVOQUEDatasetHelper)
 from single_speaker_tts_b200.synthetic import make_clips, speech_like_clip
 
 pytestmark = pytest.mark.gpu
@@ -326,3 +327,40 @@ def test_file_level_drivers_precalc_and_statistics(tmp_path):
     stats = statistics.collect_decibel_statistics(paths, batch_clips=2)
     ref = ra.collect_decibel_statistics_from_wavs([load_wav(p)[0] for p in paths], 22050)
     assert np.abs(stats - ref).max() < 1e-3
+
+
+def test_sibling_corpus_helpers_match_their_reference_recipes():
+    """datasets/blizzard_nancy.py, cmu_slt.py (LJSpeech recipe, other constants) and pavoque.py
+    (zeroed low bins + spectrogram-based row slicing) against the oracle restatements."""
+    rng = np.random.default_rng(31)
+    clips = [speech_like_clip(int(n), rng) for n in (15000, 30011)]
+    for helper, consts in ((BlizzardNancyDatasetHelper, ra.BlizzardNancyConstants), (CMUDatasetHelper, ra.CMUConstants)):
+        got = helper.features_from_wavs(clips, sampling_rate=22050)
+        for c, (mel, lin) in zip(clips, got):
+            mel_ref, lin_ref = ra.load_audio_from_wav(c, 22050, constants=consts)
+            assert mel.shape == mel_ref.shape and lin.shape == lin_ref.shape
+            assert np.abs(mel - mel_ref).max() < NORM_TOL and np.abs(lin - lin_ref).max() < NORM_TOL
+    got = PAVOQUEDatasetHelper.features_from_wavs(clips, sampling_rate=22050)
+    for c, (mel, lin) in zip(clips, got):
+        mel_ref, lin_ref = ra.pavoque_load_audio_from_wav(c, 22050)
+        assert mel.shape == mel_ref.shape and lin.shape == lin_ref.shape and mel.dtype == np.float32
+        assert np.abs(mel - mel_ref).max() < NORM_TOL and np.abs(lin - lin_ref).max() < NORM_TOL
+
+
+def test_reconstruction_error_study_matches_oracle():
+    """collect_reconstruction_error (datasets/statistics.py:146-187): per-clip MSE after n iterations;
+    compared through griffin_lim_batch with explicit initial phases (the seeded device generator has
+    no numpy equivalent), plus the seeded batch entry point for determinism."""
+    from single_speaker_tts_b200 import _runtime as rt
+    rng = np.random.default_rng(33)
+    clips = [speech_like_clip(int(n), rng) for n in (9000, 14000)]
+    win, hop = 1102, 275
+    for c in clips:
+        mag = np.abs(lc.stft(c, NFFT, hop, win))
+        ang = np.exp(2j * np.pi * np.random.RandomState(5).rand(*mag.shape))
+        ref = ra.reconstruction_error(c, 22050, 4, angles=ang)
+        _, mses = rt.griffin_lim_batch([mag], win, hop, NFFT, 4, angles=[ang], return_mse=True)
+        assert abs(mses[0] - ref) / ref < 1e-4
+    a = statistics.reconstruction_errors_from_wavs(clips, 22050, 3, seed=11)
+    b = statistics.reconstruction_errors_from_wavs(clips, 22050, 3, seed=11)
+    assert a == b and all(np.isfinite(v) and v > 0 for v in a)

@@ -161,3 +161,27 @@ def test_gl_sub_batch_split_covers_every_utterance_once():
             assert all(i1 > i0 for i0, i1 in ranges)
     sizes = [400 * (i1 - i0) for i0, i1 in _split_by_frames([400] * 300, 6000, 3)]
     assert sizes[0] == 6000 and sizes[1] == 18000 and sizes[2] == 54000 and sum(sizes) == 120000
+
+
+def test_threaded_packing_keeps_order_and_values():
+    """_hostio._pack_and_copy (staging for ragged uploads): worker groups + chunked copies must
+    reproduce np.concatenate for any mix of sizes, dtypes needing conversion and tiny chunks."""
+    import torch
+    from single_speaker_tts_b200 import _hostio
+    rng = np.random.default_rng(0)
+    arrays = [rng.standard_normal(int(n)).astype(np.float64 if i % 3 == 0 else np.float32)
+              for i, n in enumerate(rng.integers(1, 50000, size=120))]
+    lens = [len(a) for a in arrays]
+    total = sum(lens)
+    stage, out = torch.empty(total, dtype=torch.float32), torch.empty(total, dtype=torch.float32)
+    st = np.concatenate([[0], np.cumsum(lens)])
+    views = [stage.numpy()[st[k]:st[k + 1]] for k in range(len(arrays))]
+    old = _hostio._CHUNK_BYTES
+    try:
+        for chunk in (1 << 12, 1 << 18, 1 << 30):
+            _hostio._CHUNK_BYTES = chunk
+            out.zero_()
+            _hostio._pack_and_copy(views, arrays, lens, stage, out, 4)
+            assert np.array_equal(out.numpy(), np.concatenate(arrays).astype(np.float32))
+    finally:
+        _hostio._CHUNK_BYTES = old

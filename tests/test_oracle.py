@@ -149,3 +149,19 @@ def test_fixture_recipe(golden_dir):
     mag = ra.inference_postprocess(g['model_output'])
     assert mag.shape == (1025, 160) and mag.dtype == np.float32 and mag.min() > 0
     assert g['wav'].shape == (HOP * 159,)                    # 275 * (T - 1)
+
+
+def test_pavoque_recipe_restatement_shapes_and_floor():
+    """datasets/pavoque.py:104-160: zeroed bins sit on the normalised -100 dB floor (0.0 with
+    ref 24 / max 100) and the row slice comes from silence_interval_from_spectrogram as written."""
+    from oracle import reference_audio as ra
+    from single_speaker_tts_b200.synthetic import speech_like_clip
+    wav = speech_like_clip(12000, np.random.default_rng(2))
+    mel, lin = ra.pavoque_load_audio_from_wav(wav, 22050)
+    assert mel.dtype == np.float32 and lin.dtype == np.float32
+    assert mel.shape[0] == lin.shape[0] and mel.shape[1] == 400 and lin.shape[1] == 5125
+    rows = lin.reshape(-1, 1025)
+    assert np.all(rows[:, 0:8] == 0.0)
+    spec = np.zeros((5, 7)); spec[2, 3] = 1.0; spec[4, 5] = 1.0
+    assert ra.silence_interval_from_spectrogram(spec, 0.5) == (3, 5)
+    assert ra.silence_interval_from_spectrogram(spec, 2.0) is None

@@ -43,8 +43,24 @@ def pack():
         stage[o:o + m.shape[1]] = m.T
         o += m.shape[1]
 print('pack single thread (numpy copies) ms', wall(pack))
-w = torch.empty(30_000_000, dtype=torch.float32, device=dev)
-print('D2H 120 MB ms', wall(lambda: _hostio.download(w)))
+w = torch.empty(125_000_000, dtype=torch.float32, device=dev)
+wh = torch.empty(125_000_000, dtype=torch.float32, pin_memory=True)
+t = wall(lambda: wh.copy_(w, non_blocking=True))
+print('D2H 500 MB into a fixed pinned buffer: %.2f ms = %.1f GB/s' % (t, 0.5 / t * 1e3))
+t = wall(lambda: w.copy_(wh, non_blocking=True))
+print('H2D 500 MB from a fixed pinned buffer: %.2f ms = %.1f GB/s' % (t, 0.5 / t * 1e3))
+s2 = torch.cuda.Stream()
+def duplex():
+    wh.copy_(w, non_blocking=True)
+    with torch.cuda.stream(s2):
+        d.copy_(big, non_blocking=True)
+t = wall(duplex)
+print('D2H 500 MB + H2D 463 MB concurrently: %.2f ms' % t)
+def dl():
+    r = _hostio.download(w)
+    torch.cuda.current_stream().synchronize()
+    return r
+print('_hostio.download 500 MB (+ sync, result dropped): %.2f ms' % wall(dl))
 for first, growth in ((10 ** 9, 1), (24000, 1), (16000, 1), (10000, 1), (6000, 1), (6000, 2)):
     _runtime._GL_CHUNK_FRAMES, _runtime._GL_CHUNK_GROWTH = first, growth
     n = len(_runtime._split_by_frames(fb.frames, first, growth))
@@ -54,3 +70,20 @@ _runtime._GL_CHUNK_FRAMES, _runtime._GL_CHUNK_GROWTH = 10000, 1
 for it in (0, 50):
     t = wall(lambda: _runtime.griffin_lim_batch(mags, WIN, HOP, NFFT, it, seed=3))
     print('e2e n_iter=%d: %.2f ms' % (it, t))
+
+from single_speaker_tts_b200.audio import synthesis, features        # noqa: E402
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for rep in range(3):
+    synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1234)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1234)
+    e1.record()
+    torch.cuda.synchronize()
+    print('bench-style e2e (events, 5 calls): %.2f ms / call' % (e0.elapsed_time(e1) / 5))
+consts = (35.66, 100.0, 6.02, 99.89)
+for chunk in (1 << 40, 6 << 20, 3 << 20, 3 << 19):
+    _runtime._FEAT_CHUNK_SAMPLES = chunk
+    t = wall(lambda: features.features_batch(clips, NFFT, HOP, WIN, 22050, 80, 0, 8000, *consts, reduction=5))
+    print('features e2e chunk=%d samples: %.2f ms' % (chunk, t))
