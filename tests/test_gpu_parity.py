@@ -364,3 +364,32 @@ def test_reconstruction_error_study_matches_oracle():
     a = statistics.reconstruction_errors_from_wavs(clips, 22050, 3, seed=11)
     b = statistics.reconstruction_errors_from_wavs(clips, 22050, 3, seed=11)
     assert a == b and all(np.isfinite(v) and v > 0 for v in a)
+
+
+def test_pinned_inputs_take_the_zero_copy_upload_and_give_identical_results():
+    import single_speaker_tts_b200 as pkg
+    from single_speaker_tts_b200 import _hostio
+    mags, angs = _case([40, 9, 100])
+    pinned = []
+    for m in mags:
+        buf = pkg.pinned_empty((m.shape[1], m.shape[0]))      # (T, bins) C-ordered, like the model output
+        buf[:] = m.T
+        pinned.append(buf.T)                                   # the reference's (bins, T) view
+    assert _hostio._direct_sources([p.T for p in pinned], torch.float32) is not None
+    assert _hostio._direct_sources([np.ascontiguousarray(m.T) for m in mags], torch.float32) is None
+    a = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3, seed=5)
+    b = synthesis.spectrograms_to_wavs(pinned, WIN, HOP, NFFT, 3, seed=5)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    rng = np.random.default_rng(4)
+    clips = [speech_like_clip(int(n), rng) for n in (7000, 12000)]
+    pclips = []
+    for c in clips:
+        buf = pkg.pinned_empty((len(c),))
+        buf[:] = c
+        pclips.append(buf)
+    consts = (35.66, 100.0, 6.02, 99.89)
+    fa = features.features_batch(clips, NFFT, HOP, WIN, 22050, 80, 0, 8000, *consts, reduction=5)
+    fb = features.features_batch(pclips, NFFT, HOP, WIN, 22050, 80, 0, 8000, *consts, reduction=5)
+    for (m0, l0), (m1, l1) in zip(fa, fb):
+        assert np.array_equal(m0, m1) and np.array_equal(l0, l1)
