@@ -42,16 +42,18 @@ inline void split_frames(int n_frames, int tile, int min_tile, std::vector<std::
 }
 
 struct GLPlanHost {
-  int n_utts = 0, win = 0, hop = 0, span_max = 0, max_tile = 0;
+  int n_utts = 0, win = 0, hop = 0, n_fft = NFFT, span_max = 0, max_tile = 0;
   std::vector<long long> frame_off, pad_off, sample_off;
   std::vector<GLTile> tiles;
   long long total_frames = 0, total_pad = 0, total_samples = 0;
 };
 
 inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int hop, GLPlanHost& P,
-                          std::string& err) {
-  if (win < 2 || win > NFFT || hop < 1 || hop > win) { err = "need 1 <= hop <= win <= n_fft"; return false; }
-  if ((NFFT - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
+                          std::string& err, int n_fft = NFFT) {
+  if (n_fft != 2048 && n_fft != 1024 && n_fft != 512) { err = "n_fft must be 2048, 1024 or 512"; return false; }
+  if (win < 2 || win > n_fft || hop < 1 || hop > win) { err = "need 1 <= hop <= win <= n_fft"; return false; }
+  if ((n_fft - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
+  P.n_fft = n_fft;
   const int min_tile = min_tile_frames(win, hop);
   if (2 * min_tile > kTileFrames) { err = "win_length / hop_length > 5 is not supported"; return false; }
   P.n_utts = n_utts; P.win = win; P.hop = hop;
@@ -65,7 +67,7 @@ inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int h
   for (int u = 0; u < n_utts; ++u) {
     const long long T = frame_off[u + 1] - frame_off[u];
     if (T < 1 || T > (1 << 22)) { err = "every utterance needs between 1 and 2^22 frames"; return false; }
-    const long long padded = NFFT + (long long)hop * (T - 1);
+    const long long padded = n_fft + (long long)hop * (T - 1);
     P.pad_off[u + 1] = P.pad_off[u] + ((padded + 3) & ~3LL);
     P.sample_off[u + 1] = P.sample_off[u] + (long long)hop * (T - 1);
     if (T < 2) continue;  // hop * (T - 1) == 0 output samples: nothing to compute

@@ -85,12 +85,9 @@ StftTables<T> tables_view(const DeviceTables& D) {
 
 int check_config(const sstts_stft_config* cfg, bool allow_embedded) {
   if (!cfg) return fail(SSTTS_ERR_INVALID, "config is NULL");
-  if (allow_embedded) {
-    if (cfg->n_fft != 2048 && cfg->n_fft != 1024 && cfg->n_fft != 512)
-      return fail(SSTTS_ERR_INVALID, "features: n_fft must be 2048, 1024 or 512");
-  } else if (cfg->n_fft != NFFT) {
-    return fail(SSTTS_ERR_INVALID, "griffin_lim: only n_fft = 2048 is built");
-  }
+  (void)allow_embedded;
+  if (cfg->n_fft != 2048 && cfg->n_fft != 1024 && cfg->n_fft != 512)
+    return fail(SSTTS_ERR_INVALID, "n_fft must be 2048, 1024 or 512");
   if (cfg->win_length < 2 || cfg->win_length > cfg->n_fft || ((cfg->n_fft - cfg->win_length) & 1))
     return fail(SSTTS_ERR_INVALID, "win_length must be in [2, n_fft] with n_fft - win_length even");
   if (cfg->hop_length < 1) return fail(SSTTS_ERR_INVALID, "hop_length must be >= 1");
@@ -183,7 +180,7 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
   P->cfg = *cfg;
   std::string err;
   std::vector<long long> fo(frame_off_host, frame_off_host + n_utts + 1);
-  if (!build_gl_plan(n_utts, fo.data(), cfg->win_length, cfg->hop_length, P->host, err)) {
+  if (!build_gl_plan(n_utts, fo.data(), cfg->win_length, cfg->hop_length, P->host, err, cfg->n_fft)) {
     delete P;
     return fail(SSTTS_ERR_INVALID, err);
   }
@@ -240,7 +237,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   A.n_tiles = (int)H.tiles.size();
   A.tab = tables_view<T>(P->tab);
   A.mse_frame = nullptr;
-  A.win = H.win; A.hop = H.hop; A.span_max = H.span_max;
+  A.win = H.win; A.hop = H.hop; A.span_max = H.span_max; A.n_fft = H.n_fft;
 
   const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.hop, H.span_max);
   int occ_s = 0, occ_i = 0, occ_m = 0, rc;
@@ -277,7 +274,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   F.tiles = P->d_tiles; F.n_tiles = A.n_tiles;
   F.window = A.tab.window;
   F.wav_out = wav_out;
-  F.win = H.win; F.hop = H.hop;
+  F.win = H.win; F.hop = H.hop; F.n_fft = H.n_fft;
   int grid_f = n_sms * 8;
   if (grid_f > A.n_tiles) grid_f = A.n_tiles;
   gl_finalize_kernel<T, G, 256><<<grid_f, 256, sizeof(T) * (round_up4(H.win) + round_up4(H.hop)), st>>>(F);

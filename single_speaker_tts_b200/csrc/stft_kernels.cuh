@@ -123,7 +123,7 @@ SSTTS_D T* load_window_table(T* s_wtab, const T* g_window, int win, int lpad, in
 // Reciprocal window sums for samples all of whose covering frames exist ("interior"): they only
 // depend on (p - lpad) mod hop.  Same ascending-frame summation order as window_sumsq().
 template <typename T>
-SSTTS_D void fill_interior_rwss(T* s_rw, const T* s_win, int hop, int win, int tid, int nthreads) {
+SSTTS_D void fill_interior_rwss(T* s_rw, const T* s_win, int hop, int win, int tid, int nthreads, T inv_nfft) {
   for (int r = tid; r < hop; r += nthreads) {
     T acc = T(0);
     for (int j = (win - 1 - r) / hop; j >= 0; --j) {
@@ -132,7 +132,7 @@ SSTTS_D void fill_interior_rwss(T* s_rw, const T* s_win, int hop, int win, int t
     }
     // the partial-sum buffers hold n_fft x the true overlap-add sums: the 1/n_fft of the inverse
     // transform is folded in here (an exact power-of-two scaling)
-    s_rw[r] = (acc > T(SSTTS_F32_TINY) ? T(1) / acc : T(1)) * T(1.0 / NFFT);
+    s_rw[r] = (acc > T(SSTTS_F32_TINY) ? T(1) / acc : T(1)) * inv_nfft;
   }
 }
 
@@ -140,11 +140,11 @@ SSTTS_D void fill_interior_rwss(T* s_rw, const T* s_win, int hop, int win, int t
 // where it exceeds tiny, as librosa.istft does).
 template <typename T>
 SSTTS_D T normalise_ola(T v, int p, int n_frames, int hop, int win, int lpad, const T* s_win,
-                        const T* s_rw) {
+                        const T* s_rw, T inv_nfft) {
   const int x = p - lpad;
   if (x >= win - hop && x / hop <= n_frames - 1) return v * s_rw[x % hop];
   const T wss = window_sumsq<T>(p, n_frames, hop, win, lpad, s_win);
-  v *= T(1.0 / NFFT);
+  v *= inv_nfft;
   return wss > T(SSTTS_F32_TINY) ? v / wss : v;
 }
 
@@ -172,6 +172,7 @@ template <typename T> struct GLArgs {
   StftTables<T> tab;
   double* mse_frame;             // [sum T] per-frame sum_k (|S| - |E|)^2 (WANT_MSE launch only)
   int win, hop, span_max;
+  int n_fft;                     // 2048, or 1024 / 512 embedded in the 2048-point transform
 };
 
 template <typename T> SSTTS_D T fast_rsqrt(T x);
@@ -203,19 +204,19 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
 constexpr int MAX_OVERLAP = 5;  // frames covering one sample: ceil(win / hop) <= 5 (host_plan.h)
 constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
 
-// Asynchronously stage one 1025-float row into shared memory (16-byte LDGSTS for the aligned
+// Asynchronously stage one n-float row (n = 1025, 513 or 257) into shared memory (16-byte LDGSTS for the aligned
 // body, plain loads for the <= 3 + 3 ragged elements).  Element e lands at dst[e + mis]; returns
 // mis.  Completion: sstts_cp_async_wait_all() + __syncwarp().
-SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane) {
+SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane, int n = NBINS) {
   const int mis = (int)((reinterpret_cast<uintptr_t>(g) >> 2) & 3);
   const int c_lo = (mis + 3) >> 2;
-  const int c_hi = ((NBINS - 4 + mis) >> 2) + 1;      // chunks c_lo <= c < c_hi lie inside the row
+  const int c_hi = ((n - 4 + mis) >> 2) + 1;          // chunks c_lo <= c < c_hi lie inside the row
   const float* gal = g - mis;
   for (int c = c_lo + lane; c < c_hi; c += 32) sstts_cp_async16(dst + 4 * c, gal + 4 * c);
   const int head = 4 * c_lo - mis;                     // elements [0, head)
   if (lane < head) sstts_cp_async4(dst + lane + mis, g + lane);
-  const int tail0 = 4 * c_hi - mis;                    // elements [tail0, NBINS)
-  if (tail0 + lane < NBINS) sstts_cp_async4(dst + tail0 + lane + mis, g + tail0 + lane);
+  const int tail0 = 4 * c_hi - mis;                    // elements [tail0, n)
+  if (tail0 + lane < n) sstts_cp_async4(dst + tail0 + lane + mis, g + tail0 + lane);
   return mis;
 }
 
@@ -231,12 +232,17 @@ SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane) {
 // slot 31 - k2 (lane 0: its own slot 32 - k2; k = 0 pairs with the Nyquist bin; k = 512 is
 // self-conjugate).  Each lane processes its 16 low pairs and swaps results with its partner.
 // srow[k] is |S| of this frame (shared memory for the iteration kernel, global for the synth).
+// bshift > 0: a shorter transform (n_fft = 2048 >> bshift) embedded in the 2048-point one -- only
+// every (1 << bshift)-th bin exists (srow / prow are indexed by k >> bshift), the others are forced
+// to zero, which makes the inverse transform periodic with period n_fft (its first period is used).
 template <typename T, bool FROM_PHASE, bool WANT_MSE>
 SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
                            const float2* __restrict__ prow,
-                           const typename cx_of<T>::type* s_w2k, int lane, double& mse_acc) {
+                           const typename cx_of<T>::type* s_w2k, int lane, double& mse_acc, int bshift = 0) {
   typedef typename cx_of<T>::type C;
   const int partner = (32 - lane) & 31;
+  const int bmask = (1 << bshift) - 1;
+  const bool real_bin = (lane & bmask) == 0;   // k = lane + 32 k2 and 1024 - k share lane's residue
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
     const int sl_mine = k2;
@@ -245,8 +251,8 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
     const int k = lane + 32 * k2;
     const int kn = HALF - k;
     const C w = s_w2k[k];
-    const T sk = fabs((T)srow[k]);
-    const T sn = fabs((T)srow[kn]);
+    const T sk = real_bin ? fabs((T)srow[k >> bshift]) : T(0);
+    const T sn = real_bin ? fabs((T)srow[kn >> bshift]) : T(0);
     T ykr, yki, ynr, yni;
     if (!FROM_PHASE) {
       const T zr = re[sl_mine], zi = im[sl_mine];
@@ -262,13 +268,14 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
       T m2k, m2n;
       replace_magnitude<T>(xkr, xki, sk, ykr, yki, m2k);
       replace_magnitude<T>(xnr, xni, sn, ynr, yni, m2n);
-      if (WANT_MSE) {
+      if (WANT_MSE && real_bin) {
         const double ek = (double)sk - 0.5 * sqrt((double)m2k);
         const double en = (double)sn - 0.5 * sqrt((double)m2n);
         mse_acc += ek * ek + en * en;
       }
     } else {
-      const float2 pk = prow[k], pn = prow[kn];
+      float2 pk = make_float2(0.0f, 0.0f), pn = make_float2(0.0f, 0.0f);
+      if (real_bin) { pk = prow[k >> bshift]; pn = prow[kn >> bshift]; }
       ykr = sk * (T)pk.x; yki = sk * (T)pk.y;
       ynr = sn * (T)pn.x; yni = sn * (T)pn.y;
       if (lane == 0 && k2 == 0) { yki = T(0); yni = T(0); }  // ifft(...).real drops Im of DC/Nyquist
@@ -291,7 +298,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
   // k = 512 (lane 0, slot 16): X = conj(Z), Z' = conj(Y).
   if (lane == 0) {
     const int sl = 16;
-    const T s = fabs((T)srow[HALF / 2]);
+    const T s = fabs((T)srow[(HALF / 2) >> bshift]);
     T yr, yi;
     if (!FROM_PHASE) {
       T m2;
@@ -301,7 +308,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
         mse_acc += e * e;
       }
     } else {
-      const float2 p = prow[HALF / 2];
+      const float2 p = prow[(HALF / 2) >> bshift];
       yr = s * (T)p.x; yi = s * (T)p.y;
     }
     re[sl] = T(2) * yr; im[sl] = T(-2) * yi;
@@ -331,8 +338,11 @@ template <typename T> struct GLSmem {
 template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE>
 __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   typedef typename cx_of<T>::type C;
-  const G g(A.win, A.hop, NFFT);
-  const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const G g(A.win, A.hop, A.n_fft);
+  const int win = g.win(), hop = g.hop(), lpad = g.lpad(), cpad = g.cpad();
+  const int bshift = g.bin_shift();
+  const int n_bins = (HALF >> bshift) + 1;
+  const T inv_nfft = T(1.0) / T(g.nfft());
   const int mlo = lpad & ~1;          // even base of the output-frame slot (8-byte stores)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = W * 32;
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
   for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
   __syncthreads();
-  fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
+  fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT, inv_nfft);
   __syncthreads();
 
   // Tile record, loaded one tile ahead (one independent 48-byte load hidden behind the transform
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
     const int le = a > 0 ? win - hop : 0;
     const int rb = b < n_frames ? (b - a) * hop : 0x7fffffff;
     // common case: no reflection inside the span and every sample covered by a full set of frames
-    const bool plain = (span_lo >= HALF) && (span_lo + span - HALF <= L_out) && (a * hop >= win - hop) &&
+    const bool plain = (span_lo >= cpad) && (span_lo + span - cpad <= L_out) && (a * hop >= win - hop) &&
                        ((a * hop + span - 1) / hop <= n_frames - 1);
 #if SSTTS_COLUMN_STAGE
     if (plain) {
@@ -450,13 +460,13 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
 #endif
     } else {
       for (int s = tid; s < span; s += NT) {
-        int q = span_lo + s - HALF;
+        int q = span_lo + s - cpad;
         if (q < 0 || q >= L_out) q = reflect_index(q, L_out);
-        const int p = q + HALF;
+        const int p = q + cpad;
         const int sp = p - span_lo;      // reflected position relative to this tile's span
         T v = pin_own[p];
         if (sp < le || sp >= rb) v += pin_oth[p];
-        s_yin[s] = normalise_ola<T>(v, p, n_frames, hop, win, lpad, s_win, s_rw);
+        s_yin[s] = normalise_ola<T>(v, p, n_frames, hop, win, lpad, s_win, s_rw, inv_nfft);
       }
     }
   };
@@ -479,12 +489,12 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
 
     if (warp < FT) {
       const long long row = f0 + a + warp;
-      const float* mrow = A.mag + row * NBINS;
-      const float2* prow = FROM_PHASE ? A.phase0 + row * NBINS : nullptr;
+      const float* mrow = A.mag + row * n_bins;
+      const float2* prow = FROM_PHASE ? A.phase0 + row * n_bins : nullptr;
       const float* srow = mrow;
       T re[32], im[32];
       if (!FROM_PHASE) {
-        const int mis = stage_row_async(s_mag, mrow, lane);
+        const int mis = stage_row_async(s_mag, mrow, lane, n_bins);
         srow = s_mag + mis;
         const T* fin = s_yin + warp * hop - lpad;  // fin[m], m in [lpad, lpad + win)
 #pragma unroll
@@ -502,7 +512,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         __syncwarp();
       }
       double mse_acc = 0.0;
-      gl_frame_core<T, FROM_PHASE, WANT_MSE>(re, im, srow, prow, s_w2k, lane, mse_acc);
+      gl_frame_core<T, FROM_PHASE, WANT_MSE>(re, im, srow, prow, s_w2k, lane, mse_acc, bshift);
       if (WANT_MSE) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
@@ -597,20 +607,21 @@ template <typename T> struct GLFinalArgs {
   const GLTile* tiles; int n_tiles;
   const T* window;
   float* wav_out;
-  int win, hop;
+  int win, hop, n_fft;
 };
 
 template <typename T, typename G, int NT>
 __global__ void __launch_bounds__(NT) gl_finalize_kernel(const GLFinalArgs<T> A) {
-  const G g(A.win, A.hop, NFFT);
-  const int win = g.win(), hop = g.hop(), lpad = g.lpad();
+  const G g(A.win, A.hop, A.n_fft);
+  const int win = g.win(), hop = g.hop(), lpad = g.lpad(), cpad = g.cpad();
+  const T inv_nfft = T(1.0) / T(g.nfft());
   const int tid = threadIdx.x;
   SSTTS_DYN_SMEM(smem);
   T* s_win = reinterpret_cast<T*>(smem);
   T* s_rw = s_win + round_up4(win);
   for (int i = tid; i < win; i += NT) s_win[i] = A.window[i];
   __syncthreads();
-  fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT);
+  fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT, inv_nfft);
   __syncthreads();
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
     const GLTile tl = A.tiles[tile];
@@ -623,14 +634,14 @@ __global__ void __launch_bounds__(NT) gl_finalize_kernel(const GLFinalArgs<T> A)
     const T* pin_oth = (tl.parity ? A.pin0 : A.pin1) + poff;
     float* out = A.wav_out + A.sample_off[tl.utt];
     int p_lo = a * hop + lpad;
-    if (p_lo < HALF) p_lo = HALF;
-    int p_hi = (b < n_frames) ? b * hop + lpad : HALF + L_out;
-    if (p_hi > HALF + L_out) p_hi = HALF + L_out;
+    if (p_lo < cpad) p_lo = cpad;
+    int p_hi = (b < n_frames) ? b * hop + lpad : cpad + L_out;
+    if (p_hi > cpad + L_out) p_hi = cpad + L_out;
     const int left_end = (a - 1) * hop + lpad + win;
     for (int p = p_lo + tid; p < p_hi; p += NT) {
       T v = pin_own[p];
       if (a > 0 && p < left_end) v += pin_oth[p];
-      out[p - HALF] = (float)normalise_ola<T>(v, p, n_frames, hop, win, lpad, s_win, s_rw);
+      out[p - cpad] = (float)normalise_ola<T>(v, p, n_frames, hop, win, lpad, s_win, s_rw, inv_nfft);
     }
   }
 }

@@ -23,7 +23,7 @@ def load():
         lib = ctypes.CDLL(path)
         lib.emu_fft1024.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_int]
         lib.emu_griffin_lim.argtypes = [ctypes.c_int] * 4 + [_lp, _fp, _fp, ctypes.c_int, _fp, _dp,
-                                                           ctypes.c_int]
+                                                           ctypes.c_int, ctypes.c_int]
         lib.emu_stft_features.argtypes = ([ctypes.c_int] * 6 + [ctypes.c_double] * 2 +
                                           [ctypes.c_int, _lp, ctypes.c_int, _fp, _fp, _fp, _fp, _dp,
                                            _dp, ctypes.c_int] + [ctypes.c_double] * 5 + [ctypes.c_int] * 2)
@@ -41,7 +41,7 @@ def fft1024(z, inverse=False, prec=1):
     return out[0::2] + 1j * out[1::2]
 
 
-def griffin_lim(mags, angles, n_iter, prec=0, win=1102, hop=275, want_mse=False, grid_cap=3):
+def griffin_lim(mags, angles, n_iter, prec=0, win=1102, hop=275, want_mse=False, grid_cap=3, n_fft=2048):
     Ts = [m.shape[1] for m in mags]
     fo = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
     mag = np.ascontiguousarray(np.concatenate([np.asarray(m).T for m in mags], 0), dtype=np.float32)
@@ -51,11 +51,11 @@ def griffin_lim(mags, angles, n_iter, prec=0, win=1102, hop=275, want_mse=False,
     mse = np.zeros(fo[-1]) if want_mse else None
     rc = _lib.emu_griffin_lim(win, hop, prec, len(mags), fo.ctypes.data_as(_lp), mag.ctypes.data_as(_fp),
                               ph.view(np.float32).ctypes.data_as(_fp), n_iter, out.ctypes.data_as(_fp),
-                              mse.ctypes.data_as(_dp) if want_mse else None, grid_cap)
+                              mse.ctypes.data_as(_dp) if want_mse else None, grid_cap, n_fft)
     assert rc == 0
     wavs = [out[so[i]:so[i + 1]] for i in range(len(mags))]
     if want_mse:
-        return wavs, [mse[fo[i]:fo[i + 1]].sum() / (1025 * Ts[i]) for i in range(len(mags))]
+        return wavs, [mse[fo[i]:fo[i + 1]].sum() / ((1 + n_fft // 2) * Ts[i]) for i in range(len(mags))]
     return wavs
 
 

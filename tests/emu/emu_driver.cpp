@@ -61,10 +61,10 @@ void fft_test_kernel(const T* in, T* out, const typename cx_of<T>::type* tw) {
 
 template <typename T, typename G, int W>
 int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const float* mag,
-               const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap) {
+               const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap, int n_fft) {
   GLPlanHost H;
   std::string err;
-  if (!build_gl_plan(n_utts, frame_off, win, hop, H, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
+  if (!build_gl_plan(n_utts, frame_off, win, hop, H, err, n_fft)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
   if (H.tiles.empty()) return 0;
   HostTables<T> tabs;
   fill_tables<T>(win, tabs);
@@ -75,7 +75,7 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   A.frame_off = H.frame_off.data(); A.pad_off = H.pad_off.data();
   A.tiles = H.tiles.data(); A.n_tiles = (int)H.tiles.size();
   A.tab = tabs.view(); A.mse_frame = nullptr;
-  A.win = win; A.hop = hop; A.span_max = H.span_max;
+  A.win = win; A.hop = hop; A.span_max = H.span_max; A.n_fft = n_fft;
   const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
@@ -96,7 +96,7 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   F.pin0 = buf[2 * cur]; F.pin1 = buf[2 * cur + 1];
   F.frame_off = H.frame_off.data(); F.pad_off = H.pad_off.data(); F.sample_off = H.sample_off.data();
   F.tiles = H.tiles.data(); F.n_tiles = A.n_tiles; F.window = tabs.win.data(); F.wav_out = wav_out;
-  F.win = win; F.hop = hop;
+  F.win = win; F.hop = hop; F.n_fft = n_fft;
   emu::launch(dim3(grid), dim3(256), sizeof(T) * (round_up4(win) + round_up4(hop)), [&]() { gl_finalize_kernel<T, G, 256>(F); });
   return 0;
 }
@@ -174,13 +174,13 @@ int emu_fft1024(const double* in, double* out, int inverse, int prec) {
 }
 
 int emu_griffin_lim(int win, int hop, int prec, int n_utts, const long long* frame_off, const float* mag,
-                    const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap) {
-  const bool model = (win == 1102 && hop == 275);
+                    const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap, int n_fft) {
+  const bool model = (win == 1102 && hop == 275 && n_fft == 2048);
+#define GL_ARGS win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap, n_fft
   if (prec == 1)
-    return model ? emu_gl_run<double, StaticGeom<1102, 275, 2048>, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap)
-                 : emu_gl_run<double, DynGeom, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap);
-  return model ? emu_gl_run<float, StaticGeom<1102, 275, 2048>, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap)
-               : emu_gl_run<float, DynGeom, kWarps>(win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap);
+    return model ? emu_gl_run<double, StaticGeom<1102, 275, 2048>, kWarps>(GL_ARGS) : emu_gl_run<double, DynGeom, kWarps>(GL_ARGS);
+  return model ? emu_gl_run<float, StaticGeom<1102, 275, 2048>, kWarps>(GL_ARGS) : emu_gl_run<float, DynGeom, kWarps>(GL_ARGS);
+#undef GL_ARGS
 }
 
 int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels, double fmin, double fmax, int n_clips,

@@ -85,6 +85,24 @@ def test_griffin_lim_dynamic_geometry(emu):
     assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < 5e-7
 
 
+@pytest.mark.parametrize('n_fft,win,hop', [(1024, 1024, 256), (512, 400, 100)])
+def test_griffin_lim_shorter_transforms(emu, n_fft, win, hop):
+    """n_fft 1024 (audio/effects.py:71-86 calls spectrogram_to_wav with 1024 / 256 / 1024) and 512,
+    embedded in the 2048-point transform: every (2048 / n_fft)-th bin, first period of the inverse."""
+    rng = np.random.default_rng(12)
+    for T in (3, 21, 40):
+        x = speech_like_clip(hop * (T - 1) + 7, rng)
+        m = np.abs(lc.stft(x, n_fft, hop, win))
+        assert m.shape == (1 + n_fft // 2, T)
+        a = np.exp(2j * np.pi * np.random.RandomState(T).rand(*m.shape))
+        for prec, tol in ((1, 5e-7), (0, 1e-5)):
+            (w,), (mse,) = emu.griffin_lim([m], [a], 2, prec=prec, win=win, hop=hop, n_fft=n_fft, want_mse=True)
+            ref, rmse = ra.griffin_lim_v2(m, win, hop, n_fft, 2, angles=a, batched_fft=True)
+            assert w.shape == ref.shape and not np.isnan(w).any()
+            assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < tol
+            assert abs(mse - rmse) / rmse < 1e-5
+
+
 @pytest.mark.parametrize('prec,tol_lin', [(1, 5e-7), (0, 2e-3)])
 def test_feature_pipeline(emu, prec, tol_lin):
     """load_audio core (datasets/lj_speech.py:124-156): ragged clips incl. N = 1, N < hop, N == hop."""

@@ -393,3 +393,21 @@ def test_pinned_inputs_take_the_zero_copy_upload_and_give_identical_results():
     fb = features.features_batch(pclips, NFFT, HOP, WIN, 22050, 80, 0, 8000, *consts, reduction=5)
     for (m0, l0), (m1, l1) in zip(fa, fb):
         assert np.array_equal(m0, m1) and np.array_equal(l0, l1)
+
+
+def test_griffin_lim_n_fft_1024_time_stretch_geometry():
+    """audio/effects.py:71-86 reconstructs with n_fft = win = 1024, hop = 256, 25 iterations."""
+    n_fft, win, hop = 1024, 1024, 256
+    rng = np.random.default_rng(44)
+    x = speech_like_clip(hop * 60 + 11, rng)
+    m = np.abs(lc.stft(x, n_fft, hop, win))
+    a = np.exp(2j * np.pi * np.random.RandomState(9).rand(*m.shape))
+    w, mse = synthesis.griffin_lim_v2(m, win, hop, n_fft, 25, angles=a)
+    ref, rmse = ra.griffin_lim_v2(m, win, hop, n_fft, 25, angles=a, batched_fft=True)
+    assert w.shape == ref.shape == (hop * (m.shape[1] - 1),)
+    assert rel_l2(w, ref) < GL_TOL and abs(mse - rmse) / rmse < 1e-3
+    w512 = synthesis.spectrogram_to_wav(np.abs(lc.stft(x, 512, 128, 512)), 512, 128, 512, 3,
+                                        angles=np.exp(2j * np.pi * np.random.RandomState(2).rand(257, 1 + len(x) // 128)))
+    r512 = ra.spectrogram_to_wav(np.abs(lc.stft(x, 512, 128, 512)), 512, 128, 512, 3,
+                                 angles=np.exp(2j * np.pi * np.random.RandomState(2).rand(257, 1 + len(x) // 128)))
+    assert rel_l2(w512, r512) < 1e-5
