@@ -24,11 +24,24 @@ int main() {
   std::vector<double> mse((size_t)T);
   for (int prec = 0; prec < 2; ++prec) {
     if (emu_griffin_lim(1102, 275, prec, (int)frames.size(), fo.data(), mag.data(), phase.data(), 2, wav.data(),
-                        mse.data(), 3)) return 1;
+                        mse.data(), 3, 2048)) return 1;
     if (emu_griffin_lim(1024, 256, prec, (int)frames.size(), fo.data(), mag.data(), phase.data(), 1, wav.data(),
-                        nullptr, 2)) return 1;
+                        nullptr, 2, 2048)) return 1;
   }
-  std::vector<long long> lens = {1, 2, 274, 275, 276, 1500, 5000, 9000};
+  // shorter transforms embedded in the 2048-point kernels: exactly-sized (sum T, n_fft/2 + 1) inputs
+  for (int cfgi = 0; cfgi < 2; ++cfgi) {
+    const int n_fft = cfgi ? 512 : 1024, win = cfgi ? 400 : 1024, hop = cfgi ? 100 : 256, nb = n_fft / 2 + 1;
+    std::vector<float> mag_s((size_t)T * nb), phase_s((size_t)T * nb * 2);
+    for (size_t i = 0; i < mag_s.size(); ++i) mag_s[i] = mag[i];
+    for (size_t i = 0; i < phase_s.size(); ++i) phase_s[i] = phase[i];
+    long long n_s = 0;
+    for (long long t : frames) n_s += hop * (t - 1);
+    std::vector<float> wav_s((size_t)n_s);
+    for (int prec = 0; prec < 2; ++prec)
+      if (emu_griffin_lim(win, hop, prec, (int)frames.size(), fo.data(), mag_s.data(), phase_s.data(), 2, wav_s.data(),
+                          mse.data(), 3, n_fft)) return 1;
+  }
+  std::vector<long long> lens = {1, 2, 274, 275, 276, 1500, 5000, 9000, 12345, 7001};
   std::vector<long long> so(1, 0);
   for (long long n : lens) so.push_back(so.back() + n);
   std::vector<float> x((size_t)so.back());
@@ -43,7 +56,15 @@ int main() {
       std::vector<double> raw((size_t)rows * 80), mm(lens.size() * 4);
       if (emu_stft_features(n_fft, win, hop, prec, 22050, 80, 0.0, cfgi ? 11025.0 : 8000.0, (int)lens.size(), so.data(), r,
                             x.data(), spec.data(), lin.data(), mel.data(), raw.data(), mm.data(), 1, 35.66, 100.0, 6.02,
-                            99.89, 1.0, 3)) return 1;
+                            99.89, 1.0, 3, 0)) return 1;
+      // fused dB-feature mode (lin + mel only): 16-byte staging next to the ends of the exactly-sized
+      // wav buffer, padded mel table reads inside the per-warp plane
+      if (!cfgi && emu_stft_features(n_fft, win, hop, prec, 22050, 80, 0.0, 8000.0, (int)lens.size(), so.data(), r,
+                                     x.data(), nullptr, lin.data(), mel.data(), nullptr, nullptr, 1, 35.66, 100.0, 6.02,
+                                     99.89, 1.0, 3, 1)) return 1;
+      if (!cfgi && emu_stft_features(n_fft, win, hop, prec, 22050, 80, 0.0, 11025.0, (int)lens.size(), so.data(), r,
+                                     x.data(), nullptr, lin.data(), mel.data(), nullptr, nullptr, 0, 0.0, 0.0, 0.0,
+                                     0.0, 1.0, 2, 1)) return 1;
     }
   }
   std::vector<long long> cs(so.begin(), so.end() - 1), bounds(lens.size() * 2);

@@ -174,3 +174,25 @@ def test_trim_bounds_match_librosa_trim(emu):
     got = emu.trim_bounds(wavs)
     for w, b in zip(wavs, got):
         assert tuple(b) == tuple(lc.trim(w)[1])
+
+
+def test_address_sanitizer_run_of_the_emulated_kernels(tmp_path):
+    """compute-sanitizer is not available on the GPU pool, so the bounds check of the kernels is an
+    AddressSanitizer build of the emulator driver (tests/emu/asan_main.cpp): every global buffer and
+    every CTA's shared memory is an exactly-sized heap block."""
+    import os
+    import shutil
+    import subprocess
+    if os.environ.get('SSTTS_SKIP_ASAN') or shutil.which('g++') is None:
+        pytest.skip('g++ / ASAN run disabled')
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu')
+    csrc = os.path.join(os.path.dirname(here), '..', 'single_speaker_tts_b200', 'csrc')
+    exe = str(tmp_path / 'asan_main')
+    build = subprocess.run(['g++', '-O1', '-g', '-std=c++20', '-fsanitize=address', '-pthread', '-Wno-unknown-pragmas',
+                            '-I', here, '-I', csrc, os.path.join(here, 'asan_main.cpp'), '-o', exe],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and 'asan' in build.stderr.lower():
+        pytest.skip('no libasan in this toolchain')
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and 'asan run ok' in run.stdout, (run.stdout + run.stderr)[-3000:]
