@@ -275,16 +275,13 @@ def run_ours(args):
     ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan)), dtype=torch.uint8, device=dev)
     n_samples = int(lib.sstts_gl_total_samples(plan))
     wav_dev = torch.empty(n_samples, dtype=torch.float32, device=dev)
-    phase_dev = torch.empty((total_frames, N_BINS, 2), dtype=torch.float32, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def gl_step(n_iter=GL_ITERS):
-        _lib.check(lib.sstts_random_phase(ctypes.c_uint64(1234), total_frames * N_BINS,
-                                          ctypes.c_void_p(phase_dev.data_ptr()), stream))
-        _lib.check(lib.sstts_griffin_lim(plan, ctypes.c_void_p(mag_dev.data_ptr()),
-                                         ctypes.c_void_p(phase_dev.data_ptr()), n_iter,
-                                         ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(wav_dev.data_ptr()),
-                                         None, stream))
+        # seeded random initial phase drawn inside the synthesis launch (what spectrograms_to_wavs does)
+        _lib.check(lib.sstts_griffin_lim_seeded(plan, ctypes.c_void_p(mag_dev.data_ptr()), ctypes.c_uint64(1234), 0,
+                                                n_iter, ctypes.c_void_p(ws.data_ptr()),
+                                                ctypes.c_void_p(wav_dev.data_ptr()), None, stream))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -395,7 +392,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h, 'ms_per_step': gl_e2e_ms / e2e_steps,
                     'inputs': 'pinned host numpy arrays (pkg.pinned_empty), outputs numpy in pinned memory',
                     'pageable_inputs_value': total_audio * e2e_steps / (gl_e2e_pg_ms / 1000.0)},
-            'gpu_launches': args.steps * (GL_ITERS + 3),
+            'gpu_launches': args.steps * (GL_ITERS + 2),
             'roofline': {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                          'frac': gl_achieved / peak_gbs,
                          'traffic': measured_traffic('gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>'),

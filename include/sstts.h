@@ -91,6 +91,13 @@ int sstts_griffin_lim(const sstts_gl_plan* plan, const float* mag_dev, const flo
                       int n_iter, void* workspace_dev, float* wav_out_dev, double* mse_frame_dev,
                       void* stream);
 
+/* Same, with the initial phase drawn inside the first launch instead of read from memory: element
+ * i = frame_row * (n_fft/2 + 1) + bin gets the phasor sstts_random_phase_at(seed, first_element, ...)
+ * would have written at i (bit-identical results, no (sum T, bins, 2) phase buffer). */
+int sstts_griffin_lim_seeded(const sstts_gl_plan* plan, const float* mag_dev, uint64_t seed,
+                             int64_t first_element, int n_iter, void* workspace_dev, float* wav_out_dev,
+                             double* mse_frame_dev, void* stream);
+
 /* Fill n unit phasors exp(2 pi i u), u ~ U[0, 1) from a counter-based generator keyed by seed
  * (batched extension: replaces the host-side np.random.rand of audio/synthesis.py:85). */
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream);

@@ -53,6 +53,9 @@ SIGNATURES = {
     'sstts_griffin_lim': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p]),
+    'sstts_griffin_lim_seeded': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64,
+                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p]),
     'sstts_random_phase': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p,
                                           ctypes.c_void_p]),
     'sstts_random_phase_at': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,

@@ -255,18 +255,21 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                     ref_db, max_db, power = [float(v) for v in denormalize]
                     _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), tf * n_bins, ref_db, max_db, power,
                                                                _ptr(mag_dev), _ptr(flag_dev), _stream_ptr()))
-                if phase_dev is None:
-                    phase_dev = torch.empty((tf, n_bins, 2), dtype=torch.float32, device=dev)
-                    _lib.check(lib.sstts_random_phase_at(ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
-                                                         int(frame_base[i0]) * n_bins, tf * n_bins,
-                                                         _ptr(phase_dev), _stream_ptr()))
                 ts = int(lib.sstts_gl_total_samples(plan.handle))
                 so = np.ctypeslib.as_array(lib.sstts_gl_sample_offsets(plan.handle), shape=(i1 - i0 + 1,)).copy()
                 ws = torch.empty(int(lib.sstts_gl_workspace_bytes(plan.handle)), dtype=torch.uint8, device=dev)
                 wav_dev = torch.empty(max(ts, 1), dtype=torch.float32, device=dev)
                 mse_dev = torch.zeros(tf, dtype=torch.float64, device=dev) if return_mse else None
-                _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
-                                                 _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
+                if phase_dev is not None:
+                    _lib.check(lib.sstts_griffin_lim(plan.handle, _ptr(mag_dev), _ptr(phase_dev), int(n_iter),
+                                                     _ptr(ws), _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
+                else:
+                    # the first launch draws the phase itself: element index = global frame row * bins + bin,
+                    # so the result does not depend on how the batch was split
+                    _lib.check(lib.sstts_griffin_lim_seeded(plan.handle, _ptr(mag_dev),
+                                                            ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                                            int(frame_base[i0]) * n_bins, int(n_iter), _ptr(ws),
+                                                            _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
                 # results go back on their own stream so that the next iterations start at once
                 if piped:
                     done = torch.cuda.Event()

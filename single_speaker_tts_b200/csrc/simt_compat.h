@@ -37,6 +37,8 @@ __device__ __forceinline__ float sstts_log2_ftz(float x) {       // bare MUFU.LG
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float sstts_sin_approx(float x) { return __sinf(x); }   // MUFU.SIN, |x| <= pi
+__device__ __forceinline__ float sstts_cos_approx(float x) { return __cosf(x); }
 __device__ __forceinline__ float sstts_rsqrt_approx(float x) {   // MUFU.RSQ, denormals flushed
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

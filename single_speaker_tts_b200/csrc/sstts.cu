@@ -221,8 +221,9 @@ const int64_t* sstts_gl_sample_offsets(const sstts_gl_plan* P) {
 namespace {
 
 template <typename T, typename G, int W>
-int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase0, int n_iter,
-                    void* workspace, float* wav_out, double* mse_frame, cudaStream_t st) {
+int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase0, uint64_t seed,
+                    int64_t first, int n_iter, void* workspace, float* wav_out, double* mse_frame,
+                    cudaStream_t st) {
   const GLPlanHost& H = P->host;
   if (H.tiles.empty()) return 0;
   T* ws = reinterpret_cast<T*>(workspace);
@@ -231,6 +232,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   GLArgs<T> A;
   A.mag = mag;
   A.phase0 = reinterpret_cast<const float2*>(phase0);
+  A.phase_seed = seed; A.phase_first = first;
   A.frame_off = P->d_frame_off;
   A.pad_off = P->d_pad_off;
   A.tiles = P->d_tiles;
@@ -282,20 +284,11 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   return 0;
 }
 
-// counter-based uniform phase: splitmix64 of (seed, index) -> 24-bit uniform -> unit phasor
+// stand-alone generator of the batched API's initial phase (seeded_phasor, stft_kernels.cuh)
 __global__ void random_phase_kernel(unsigned long long seed, long long first, long long n, float2* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(first + i + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z = z ^ (z >> 31);
-    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // [0, 1)
-    float s, c;
-    sincospif(2.0f * u, &s, &c);
-    out[i] = make_float2(c, s);
-  }
+  for (; i < n; i += stride) out[i] = seeded_phasor(seed, first + i);
 }
 
 // tacotron/inference.py:94-101,175: normalised model output -> dB (inv_normalize_decibel) ->
@@ -396,25 +389,34 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
 
 extern "C" {
 
-int sstts_griffin_lim(const sstts_gl_plan* P, const float* mag_dev, const float* phase0_dev,
-                      int n_iter, void* workspace_dev, float* wav_out_dev, double* mse_frame_dev,
-                      void* stream) {
-  if (!P || !mag_dev || !phase0_dev || !workspace_dev || n_iter < 0)
-    return fail(SSTTS_ERR_INVALID, "bad griffin_lim arguments");
+static int griffin_lim_dispatch(const sstts_gl_plan* P, const float* mag_dev, const float* phase0_dev,
+                                uint64_t seed, int64_t first, int n_iter, void* workspace_dev,
+                                float* wav_out_dev, double* mse_frame_dev, void* stream) {
+  if (!P || !mag_dev || !workspace_dev || n_iter < 0) return fail(SSTTS_ERR_INVALID, "bad griffin_lim arguments");
   if (P->host.total_samples > 0 && !wav_out_dev) return fail(SSTTS_ERR_INVALID, "wav_out_dev is NULL");
   if (mse_frame_dev && n_iter < 1) return fail(SSTTS_ERR_INVALID, "mse needs n_iter >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
-  if (P->cfg.precision == SSTTS_F64) {
-    return model ? run_griffin_lim<double, ModelGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
-                                                         wav_out_dev, mse_frame_dev, st)
-                 : run_griffin_lim<double, DynGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
-                                                       wav_out_dev, mse_frame_dev, st);
-  }
-  return model ? run_griffin_lim<float, ModelGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
-                                                           wav_out_dev, mse_frame_dev, st)
-               : run_griffin_lim<float, DynGeom, kWarps>(P, mag_dev, phase0_dev, n_iter, workspace_dev,
-                                                         wav_out_dev, mse_frame_dev, st);
+#define GL_CALL(T, G) run_griffin_lim<T, G, kWarps>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \
+                                                    wav_out_dev, mse_frame_dev, st)
+  if (P->cfg.precision == SSTTS_F64) return model ? GL_CALL(double, ModelGeom) : GL_CALL(double, DynGeom);
+  return model ? GL_CALL(float, ModelGeom) : GL_CALL(float, DynGeom);
+#undef GL_CALL
+}
+
+int sstts_griffin_lim(const sstts_gl_plan* P, const float* mag_dev, const float* phase0_dev,
+                      int n_iter, void* workspace_dev, float* wav_out_dev, double* mse_frame_dev,
+                      void* stream) {
+  if (!phase0_dev) return fail(SSTTS_ERR_INVALID, "phase0_dev is NULL (use sstts_griffin_lim_seeded)");
+  return griffin_lim_dispatch(P, mag_dev, phase0_dev, 0, 0, n_iter, workspace_dev, wav_out_dev, mse_frame_dev, stream);
+}
+
+int sstts_griffin_lim_seeded(const sstts_gl_plan* P, const float* mag_dev, uint64_t seed, int64_t first_element,
+                             int n_iter, void* workspace_dev, float* wav_out_dev, double* mse_frame_dev,
+                             void* stream) {
+  if (first_element < 0) return fail(SSTTS_ERR_INVALID, "first_element must be >= 0");
+  return griffin_lim_dispatch(P, mag_dev, nullptr, seed, first_element, n_iter, workspace_dev, wav_out_dev,
+                              mse_frame_dev, stream);
 }
 
 int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_dev, void* stream) {

@@ -162,7 +162,9 @@ struct alignas(16) GLTile {
 
 template <typename T> struct GLArgs {
   const float* mag;              // (sum T, 1025) frame-major |S|
-  const float2* phase0;          // (sum T, 1025) initial unit phasors (FROM_PHASE launch only)
+  const float2* phase0;          // (sum T, bins) initial unit phasors (FROM_PHASE launch only), or nullptr:
+  unsigned long long phase_seed; //   then element i = row * bins + bin gets seeded_phasor(phase_seed,
+  long long phase_first;         //   phase_first + i)
   const T* pin0; const T* pin1;  // partial overlap-add sums of the previous step, by tile parity
   T* pout0; T* pout1;            // ... of this step
   const long long* frame_off;    // [n_utts + 1]
@@ -220,6 +222,26 @@ SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane, i
   return mis;
 }
 
+// Counter-based initial phase of the batched API (replaces np.random.rand at audio/synthesis.py:85):
+// element index -> two rounds of the murmur3 32-bit finaliser over (index, seed) -> 24-bit uniform u
+// -> exp(2 pi i (u - 1/2)) with the SFU sine / cosine (|error| ~ 5e-7: the phase only has to be
+// random).  Shared by the stand-alone generator (sstts_random_phase_at) and the synthesis launch
+// that draws the phase itself, so both give the same bits.
+SSTTS_D unsigned fmix32(unsigned h) {
+  h ^= h >> 16; h *= 0x85ebca6bu;
+  h ^= h >> 13; h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+SSTTS_D float2 seeded_phasor(unsigned long long seed, long long index) {
+  const unsigned lo = (unsigned)index, hi = (unsigned)((unsigned long long)index >> 32);
+  unsigned h = fmix32(lo ^ (unsigned)seed);
+  h = fmix32(h ^ hi ^ (unsigned)(seed >> 32) ^ 0x9e3779b9u);
+  const float a = ((float)(h >> 8) * (1.0f / 16777216.0f) - 0.5f) * 6.283185307179586f;   // [-pi, pi)
+  float2 r; r.x = sstts_cos_approx(a); r.y = sstts_sin_approx(a);
+  return r;
+}
+
 // The per-frame core of one Griffin-Lim step, on the packed spectrum held by the warp.
 //   in  (FROM_PHASE = false): re/im = Z = FFT1024(z), element 32 r + lane in slot r
 //   out: re/im = 2 Z' (packed spectrum of |S| * E/|E|), same slots
@@ -238,7 +260,8 @@ SSTTS_D int stage_row_async(float* dst, const float* __restrict__ g, int lane, i
 template <typename T, bool FROM_PHASE, bool WANT_MSE>
 SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
                            const float2* __restrict__ prow,
-                           const typename cx_of<T>::type* s_w2k, int lane, double& mse_acc, int bshift = 0) {
+                           const typename cx_of<T>::type* s_w2k, int lane, double& mse_acc, int bshift = 0,
+                           unsigned long long phase_seed = 0, long long phase_base = 0) {
   typedef typename cx_of<T>::type C;
   const int partner = (32 - lane) & 31;
   const int bmask = (1 << bshift) - 1;
@@ -275,7 +298,13 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
       }
     } else {
       float2 pk = make_float2(0.0f, 0.0f), pn = make_float2(0.0f, 0.0f);
-      if (real_bin) { pk = prow[k >> bshift]; pn = prow[kn >> bshift]; }
+      if (real_bin) {
+        if (prow) { pk = prow[k >> bshift]; pn = prow[kn >> bshift]; }
+        else {   // prow == nullptr: the phase is drawn here (element index = phase_base + bin)
+          pk = seeded_phasor(phase_seed, phase_base + (k >> bshift));
+          pn = seeded_phasor(phase_seed, phase_base + (kn >> bshift));
+        }
+      }
       ykr = sk * (T)pk.x; yki = sk * (T)pk.y;
       ynr = sn * (T)pn.x; yni = sn * (T)pn.y;
       if (lane == 0 && k2 == 0) { yki = T(0); yni = T(0); }  // ifft(...).real drops Im of DC/Nyquist
@@ -308,7 +337,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
         mse_acc += e * e;
       }
     } else {
-      const float2 p = prow[(HALF / 2) >> bshift];
+      const float2 p = prow ? prow[(HALF / 2) >> bshift] : seeded_phasor(phase_seed, phase_base + ((HALF / 2) >> bshift));
       yr = s * (T)p.x; yi = s * (T)p.y;
     }
     re[sl] = T(2) * yr; im[sl] = T(-2) * yi;
@@ -490,7 +519,7 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
     if (warp < FT) {
       const long long row = f0 + a + warp;
       const float* mrow = A.mag + row * n_bins;
-      const float2* prow = FROM_PHASE ? A.phase0 + row * n_bins : nullptr;
+      const float2* prow = (FROM_PHASE && A.phase0) ? A.phase0 + row * n_bins : nullptr;
       const float* srow = mrow;
       T re[32], im[32];
       if (!FROM_PHASE) {
@@ -512,7 +541,8 @@ __global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
         __syncwarp();
       }
       double mse_acc = 0.0;
-      gl_frame_core<T, FROM_PHASE, WANT_MSE>(re, im, srow, prow, s_w2k, lane, mse_acc, bshift);
+      gl_frame_core<T, FROM_PHASE, WANT_MSE>(re, im, srow, prow, s_w2k, lane, mse_acc, bshift, A.phase_seed,
+                                             A.phase_first + row * n_bins);
       if (WANT_MSE) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);

@@ -147,6 +147,8 @@ static inline float sstts_sqrt_approx(float x) { return sqrtf(x); }
 static inline float sstts_rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float sstts_log2_approx(float x) { return log2f(x); }
 static inline float sstts_log2_ftz(float x) { return log2f(x); }
+static inline float sstts_sin_approx(float x) { return sinf(x); }
+static inline float sstts_cos_approx(float x) { return cosf(x); }
 static inline void sstts_cp_async_commit() {}
 static inline void sstts_cp_async_wait_group1() {}
 template <typename V> static inline V __ldg(const V* p) { return *p; }

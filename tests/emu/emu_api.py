@@ -45,12 +45,12 @@ def griffin_lim(mags, angles, n_iter, prec=0, win=1102, hop=275, want_mse=False,
     Ts = [m.shape[1] for m in mags]
     fo = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
     mag = np.ascontiguousarray(np.concatenate([np.asarray(m).T for m in mags], 0), dtype=np.float32)
-    ph = np.ascontiguousarray(np.concatenate([a.T for a in angles], 0).astype(np.complex64))
+    ph = None if angles is None else np.ascontiguousarray(np.concatenate([a.T for a in angles], 0).astype(np.complex64))
     so = np.concatenate([[0], np.cumsum([hop * (t - 1) for t in Ts])]).astype(np.int64)
     out = np.full(max(1, so[-1]), np.nan, dtype=np.float32)
     mse = np.zeros(fo[-1]) if want_mse else None
     rc = _lib.emu_griffin_lim(win, hop, prec, len(mags), fo.ctypes.data_as(_lp), mag.ctypes.data_as(_fp),
-                              ph.view(np.float32).ctypes.data_as(_fp), n_iter, out.ctypes.data_as(_fp),
+                              None if ph is None else ph.view(np.float32).ctypes.data_as(_fp), n_iter, out.ctypes.data_as(_fp),
                               mse.ctypes.data_as(_dp) if want_mse else None, grid_cap, n_fft)
     assert rc == 0
     wavs = [out[so[i]:so[i + 1]] for i in range(len(mags))]

@@ -72,6 +72,7 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   T* buf[4] = {ws.data(), ws.data() + H.total_pad, ws.data() + 2 * H.total_pad, ws.data() + 3 * H.total_pad};
   GLArgs<T> A;
   A.mag = mag; A.phase0 = reinterpret_cast<const float2*>(phase0);
+  A.phase_seed = 0x5eedULL; A.phase_first = 0;     // used when phase0 == nullptr
   A.frame_off = H.frame_off.data(); A.pad_off = H.pad_off.data();
   A.tiles = H.tiles.data(); A.n_tiles = (int)H.tiles.size();
   A.tab = tabs.view(); A.mse_frame = nullptr;
