@@ -17,6 +17,13 @@ namespace sstts {
 #endif
 constexpr int kTileFrames = SSTTS_WARPS;
 constexpr int kWarps = SSTTS_WARPS;
+// Griffin-Lim float32 kernels: warps per CTA = frames per tile.  Measured (tools/ab_bench.sh): 8 warps,
+// 2 CTAs / SM, 128 registers: 0.605 ms per iteration launch; 9 warps (18 resident warps, but the
+// register file is split four ways, so 96 registers / thread and spills): 0.664 ms.
+#ifndef SSTTS_GL_WARPS
+#define SSTTS_GL_WARPS 8
+#endif
+constexpr int kGlWarps = SSTTS_GL_WARPS;
 
 // Smallest tile of a multi-tile utterance: (ft + 1) * hop >= win keeps same-parity spans and a
 // tile's two edge regions disjoint (>= 4 for win 1102 / hop 275).
@@ -49,13 +56,13 @@ struct GLPlanHost {
 };
 
 inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int hop, GLPlanHost& P,
-                          std::string& err, int n_fft = NFFT) {
+                          std::string& err, int n_fft = NFFT, int tile_frames = kTileFrames) {
   if (n_fft != 2048 && n_fft != 1024 && n_fft != 512) { err = "n_fft must be 2048, 1024 or 512"; return false; }
   if (win < 2 || win > n_fft || hop < 1 || hop > win) { err = "need 1 <= hop <= win <= n_fft"; return false; }
   if ((n_fft - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
   P.n_fft = n_fft;
   const int min_tile = min_tile_frames(win, hop);
-  if (2 * min_tile > kTileFrames) { err = "win_length / hop_length > 5 is not supported"; return false; }
+  if (2 * min_tile > tile_frames) { err = "win_length / hop_length > 5 is not supported"; return false; }
   P.n_utts = n_utts; P.win = win; P.hop = hop;
   P.frame_off.assign(frame_off, frame_off + n_utts + 1);
   P.pad_off.assign(n_utts + 1, 0);
@@ -71,7 +78,7 @@ inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int h
     P.pad_off[u + 1] = P.pad_off[u] + ((padded + 3) & ~3LL);
     P.sample_off[u + 1] = P.sample_off[u] + (long long)hop * (T - 1);
     if (T < 2) continue;  // hop * (T - 1) == 0 output samples: nothing to compute
-    split_frames((int)T, kTileFrames, min_tile, parts);
+    split_frames((int)T, tile_frames, min_tile, parts);
     for (size_t i = 0; i < parts.size(); ++i) {
       GLTile t; t.utt = u; t.a = parts[i].first; t.b = parts[i].second; t.parity = (int)(i & 1);
       t.f0 = frame_off[u]; t.poff = P.pad_off[u]; t.n_frames = (int)T; t.reserved = 0; t.soff = P.sample_off[u];

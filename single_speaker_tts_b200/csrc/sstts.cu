@@ -180,7 +180,8 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
   P->cfg = *cfg;
   std::string err;
   std::vector<long long> fo(frame_off_host, frame_off_host + n_utts + 1);
-  if (!build_gl_plan(n_utts, fo.data(), cfg->win_length, cfg->hop_length, P->host, err, cfg->n_fft)) {
+  if (!build_gl_plan(n_utts, fo.data(), cfg->win_length, cfg->hop_length, P->host, err, cfg->n_fft,
+                     cfg->precision == SSTTS_F64 ? kWarps : kGlWarps)) {
     delete P;
     return fail(SSTTS_ERR_INVALID, err);
   }
@@ -397,10 +398,10 @@ static int griffin_lim_dispatch(const sstts_gl_plan* P, const float* mag_dev, co
   if (mse_frame_dev && n_iter < 1) return fail(SSTTS_ERR_INVALID, "mse needs n_iter >= 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
-#define GL_CALL(T, G) run_griffin_lim<T, G, kWarps>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \
-                                                    wav_out_dev, mse_frame_dev, st)
-  if (P->cfg.precision == SSTTS_F64) return model ? GL_CALL(double, ModelGeom) : GL_CALL(double, DynGeom);
-  return model ? GL_CALL(float, ModelGeom) : GL_CALL(float, DynGeom);
+#define GL_CALL(T, G, W) run_griffin_lim<T, G, W>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \
+                                                  wav_out_dev, mse_frame_dev, st)
+  if (P->cfg.precision == SSTTS_F64) return model ? GL_CALL(double, ModelGeom, kWarps) : GL_CALL(double, DynGeom, kWarps);
+  return model ? GL_CALL(float, ModelGeom, kGlWarps) : GL_CALL(float, DynGeom, kGlWarps);
 #undef GL_CALL
 }
 

@@ -151,7 +151,7 @@ SSTTS_D T normalise_ola(T v, int p, int n_frames, int hop, int win, int lpad, co
 // =============================================================================================
 // Griffin-Lim
 // =============================================================================================
-// frames [a, b) of utterance utt, b - a <= 8.  The record carries the utterance's offsets so that a
+// frames [a, b) of utterance utt, b - a <= warps per CTA.  The record carries the utterance's offsets so that a
 // kernel needs ONE independent 48-byte load per tile instead of a tile -> utterance -> offsets chain.
 struct alignas(16) GLTile {
   int utt, a, b, parity;
@@ -365,7 +365,7 @@ template <typename T> struct GLSmem {
 // One Griffin-Lim step over all tiles.  FROM_PHASE = true is the initial synthesis from the
 // random phase (no analysis half).  W warps per CTA, one frame per warp, tiles of <= W frames.
 template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE>
-__global__ void __launch_bounds__(W * 32) gl_step_kernel(const GLArgs<T> A) {
+__global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel(const GLArgs<T> A) {
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, A.n_fft);
   const int win = g.win(), hop = g.hop(), lpad = g.lpad(), cpad = g.cpad();
@@ -741,8 +741,11 @@ constexpr int FEAT_PLANE_ELEMS = 1056;  // >= XPLANE_ELEMS and >= NBINS floats
 // copies.  Results differ from kGeneric by float32 rounding only (~1e-7 of the normalised value).
 struct FeatMode { enum { kGeneric = 0, kDbFeatures = 1 }; };
 
+#ifndef SSTTS_FEAT_MINBLOCKS
+#define SSTTS_FEAT_MINBLOCKS 2
+#endif
 template <typename T, typename G, int W, int MODE>
-__global__ void __launch_bounds__(W * 32) stft_feature_kernel(const FeatArgs<T> A) {
+__global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS : 1) stft_feature_kernel(const FeatArgs<T> A) {
   constexpr bool FAST = MODE == FeatMode::kDbFeatures;
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, A.n_fft);

@@ -64,7 +64,7 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
                const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap, int n_fft) {
   GLPlanHost H;
   std::string err;
-  if (!build_gl_plan(n_utts, frame_off, win, hop, H, err, n_fft)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
+  if (!build_gl_plan(n_utts, frame_off, win, hop, H, err, n_fft, W)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
   if (H.tiles.empty()) return 0;
   HostTables<T> tabs;
   fill_tables<T>(win, tabs);
@@ -180,7 +180,7 @@ int emu_griffin_lim(int win, int hop, int prec, int n_utts, const long long* fra
 #define GL_ARGS win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap, n_fft
   if (prec == 1)
     return model ? emu_gl_run<double, StaticGeom<1102, 275, 2048>, kWarps>(GL_ARGS) : emu_gl_run<double, DynGeom, kWarps>(GL_ARGS);
-  return model ? emu_gl_run<float, StaticGeom<1102, 275, 2048>, kWarps>(GL_ARGS) : emu_gl_run<float, DynGeom, kWarps>(GL_ARGS);
+  return model ? emu_gl_run<float, StaticGeom<1102, 275, 2048>, kGlWarps>(GL_ARGS) : emu_gl_run<float, DynGeom, kGlWarps>(GL_ARGS);
 #undef GL_ARGS
 }
 
