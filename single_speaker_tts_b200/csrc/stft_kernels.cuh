@@ -575,7 +575,27 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       const int dl = lpad - mlo;
       const int pe = L.plane_elems;
       T* dst = pout_own + span_lo;
-      for (int r = tid; r < hop; r += NT) {
+      // residues beyond the first NT (hop 275 vs 256 threads: 19 of them) would keep one warp busy
+      // for a whole second pass while the others wait at the barrier: they are spread over all
+      // threads in row form instead, one output sample per thread
+      const int r_cols = hop <= NT ? hop : (hop / NT) * NT;
+      const int n_left = hop - r_cols;
+      if (n_left > 0) {
+        constexpr int NQ = W + MAX_OVERLAP - 1;
+        for (int t = tid; t < n_left * NQ; t += NT) {
+          const int q = t / n_left, r = r_cols + t % n_left;
+          const int s = q * hop + r;
+          if (s < span) {
+            T acc = T(0);
+            for (int j = MAX_OVERLAP - 1; j >= 0; --j) {      // ascending frame order f = q - j
+              const int f = q - j, off = r + j * hop;
+              if (f >= 0 && f < FT && off < win) acc += s_planes[f * pe + off + dl];
+            }
+            dst[s] = acc;
+          }
+        }
+      }
+      for (int r = tid; r < r_cols; r += NT) {
         T acc[W + MAX_OVERLAP - 1];
 #pragma unroll
         for (int q = 0; q < W + MAX_OVERLAP - 1; ++q) acc[q] = T(0);
