@@ -23,6 +23,10 @@ __device__ __forceinline__ void sstts_cp_async4(void* smem_dst, const void* gmem
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src));
 }
+// pull one 128-byte line towards L2 (no register, no scoreboard entry)
+__device__ __forceinline__ void sstts_prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void sstts_cp_async_commit() {
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }

@@ -536,6 +536,24 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
           re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
           im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
         }
+#ifndef SSTTS_STAGE_PREFETCH
+#define SSTTS_STAGE_PREFETCH 1
+#endif
+        if (SSTTS_STAGE_PREFETCH && next < A.n_tiles) {
+          // the next tile's span of both parity buffers is pulled into L2 while this tile is transformed
+          // (one 128-byte line per thread, no registers held), so the synchronous staging after the
+          // gather waits for an L2 hit instead of DRAM.  Placed after the window load: the tile record
+          // loaded at the top of the round has arrived by now; tiles with fewer than 6 frames issue
+          // only part of the hints
+          const int nspan = (nxt.b - nxt.a - 1) * hop + win;
+          const int lines = (nspan * (int)sizeof(T) + 127) / 128 + 1;
+          const long long base = nxt.poff + nxt.a * hop + lpad;
+          const int line = tid < lines ? tid : tid - lines;
+          if (tid < 2 * lines) {
+            const T* src = ((tid < lines) == (nxt.parity != 0) ? A.pin1 : A.pin0) + base;
+            sstts_prefetch_l2(reinterpret_cast<const char*>(src) + 128 * line);
+          }
+        }
         warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
         sstts_cp_async_wait_all();
         __syncwarp();

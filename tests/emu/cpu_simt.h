@@ -150,6 +150,7 @@ static inline float sstts_log2_ftz(float x) { return log2f(x); }
 static inline float sstts_sin_approx(float x) { return sinf(x); }
 static inline float sstts_cos_approx(float x) { return cosf(x); }
 static inline void sstts_cp_async_commit() {}
+static inline void sstts_prefetch_l2(const void*) {}
 static inline void sstts_cp_async_wait_group1() {}
 template <typename V> static inline V __ldg(const V* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
