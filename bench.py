@@ -239,6 +239,24 @@ def run_ours(args):
         barrier()
         return max_over_ranks(ms)
 
+    def timed_calls(fn, steps, warmup):
+        """Like timed(), plus this rank's per-call times (an event after every call): the end-to-end
+        calls synchronise internally, so the per-call list shows host-side hiccups (page-locked
+        allocations, other tenants of the host) that the total hides."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[steps])
+        per_call = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)]
+        barrier()
+        return max_over_ranks(ms), per_call
+
     # ---- workload: configs[1]/[2], 256 ragged clips per rank (weak scaling) ----
     # weak scaling: every rank owns the same 256-clip workload (same seed), so per-GPU work is fixed exactly
     clips = make_clips(N_UTTS, seed=1, pool=16)
@@ -306,7 +324,7 @@ def run_ours(args):
         synthesis.spectrograms_to_wavs(mags_pageable, WIN, HOP, NFFT, GL_ITERS, seed=1234)
 
     e2e_steps = max(1, min(args.steps, 5))
-    gl_e2e_ms = timed(gl_e2e, e2e_steps, max(1, args.warmup))
+    gl_e2e_ms, gl_e2e_calls = timed_calls(gl_e2e, e2e_steps, max(1, args.warmup))
     gl_e2e_value = total_audio * e2e_steps / (gl_e2e_ms / 1000.0)
     gl_e2e_pg_ms = timed(gl_e2e_pageable, e2e_steps, max(1, args.warmup))
     h2d = total_frames * N_BINS * 4
@@ -355,12 +373,13 @@ def run_ours(args):
     def feat_e2e_pageable():
         feat_api.features_batch(clips, NFFT, HOP, WIN, SR, 80, 0, 8000, *consts, reduction=5)
 
-    f_e2e_ms = timed(feat_e2e, e2e_steps, max(1, args.warmup))
+    f_e2e_ms, f_e2e_calls = timed_calls(feat_e2e, e2e_steps, max(1, args.warmup))
     f_e2e_pg_ms = timed(feat_e2e_pageable, e2e_steps, max(1, args.warmup))
     rows5 = sum(-(-t // 5) * 5 for t in frames)
     feat_e2e = {'value': sum_over_ranks(audio_in_s) * e2e_steps / (f_e2e_ms / 1000.0), 'unit': 'audio-s/s',
                 'h2d_bytes_per_step': int(sum(len(c) for c in clips)) * 4,
                 'd2h_bytes_per_step': rows5 * (N_BINS + 80) * 4, 'inputs': 'pinned host numpy arrays',
+                'ms_per_step': f_e2e_ms / e2e_steps, 'per_call_ms_rank0': f_e2e_calls,
                 'pageable_inputs_value': sum_over_ranks(audio_in_s) * e2e_steps / (f_e2e_pg_ms / 1000.0)}
 
     # ---- CPU baseline on rank 0 (oracle, bounded sample) ----
@@ -391,6 +410,7 @@ def run_ours(args):
             'e2e': {'value': gl_e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': gl_e2e_ms / e2e_steps,
                     'inputs': 'pinned host numpy arrays (pkg.pinned_empty), outputs numpy in pinned memory',
+                    'per_call_ms_rank0': gl_e2e_calls,
                     'pageable_inputs_value': total_audio * e2e_steps / (gl_e2e_pg_ms / 1000.0)},
             'gpu_launches': args.steps * (GL_ITERS + 2),
             'roofline': {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',

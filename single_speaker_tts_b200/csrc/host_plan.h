@@ -20,6 +20,14 @@ constexpr int kWarps = SSTTS_WARPS;
 // Griffin-Lim float32 kernels: warps per CTA = frames per tile.  Measured (tools/ab_bench.sh): 8 warps,
 // 2 CTAs / SM, 128 registers: 0.605 ms per iteration launch; 9 warps (18 resident warps, but the
 // register file is split four ways, so 96 registers / thread and spills): 0.664 ms.
+// float64 feature kernel: warps per CTA (a tile still holds kTileFrames frames: with fewer warps
+// every warp transforms several frames of the tile).  ~250 registers / thread allow 8 warps per SM
+// either as one CTA of 8 (0.74 ms per 256-clip batch) or as two independent CTAs of 4 whose phases
+// interleave (0.63 ms, tools/ab_bench.sh).
+#ifndef SSTTS_FEAT_WARPS_F64
+#define SSTTS_FEAT_WARPS_F64 4
+#endif
+constexpr int kFeatWarpsF64 = SSTTS_FEAT_WARPS_F64;
 #ifndef SSTTS_GL_WARPS
 #define SSTTS_GL_WARPS 8
 #endif

@@ -546,9 +546,9 @@ int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const ss
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   const bool stats = is_stats_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   if (P->cfg.precision == SSTTS_F64) {
-    if (model) return run_features<double, ModelGeom, kWarps>(P, wav_dev, out, st);
-    if (stats) return run_features<double, StatsGeom, kWarps>(P, wav_dev, out, st);
-    return run_features<double, DynGeom, kWarps>(P, wav_dev, out, st);
+    if (model) return run_features<double, ModelGeom, kFeatWarpsF64>(P, wav_dev, out, st);
+    if (stats) return run_features<double, StatsGeom, kFeatWarpsF64>(P, wav_dev, out, st);
+    return run_features<double, DynGeom, kFeatWarpsF64>(P, wav_dev, out, st);
   }
   if (model) return run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st);
   if (stats) return run_features<float, StatsGeom, kWarps>(P, wav_dev, out, st);

@@ -783,7 +783,7 @@ struct FeatMode { enum { kGeneric = 0, kDbFeatures = 1 }; };
 #define SSTTS_FEAT_MINBLOCKS 2
 #endif
 template <typename T, typename G, int W, int MODE>
-__global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS : 1) stft_feature_kernel(const FeatArgs<T> A) {
+__global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS : (W <= 4 ? 2 : 1)) stft_feature_kernel(const FeatArgs<T> A) {
   constexpr bool FAST = MODE == FeatMode::kDbFeatures;
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, A.n_fft);

@@ -192,9 +192,9 @@ int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels,
   const bool stats = (n_fft == 1024 && win == 1024 && hop == 256);
 #define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap, fast_mode
   if (prec == 1) {
-    if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
-    if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
-    return emu_feat_run<double, DynGeom, kWarps>(FEAT_ARGS);
+    if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, kFeatWarpsF64>(FEAT_ARGS);
+    if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, kFeatWarpsF64>(FEAT_ARGS);
+    return emu_feat_run<double, DynGeom, kFeatWarpsF64>(FEAT_ARGS);
   }
   if (model) return emu_feat_run<float, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
   if (stats) return emu_feat_run<float, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
