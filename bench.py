@@ -324,7 +324,22 @@ def run_ours(args):
         synthesis.spectrograms_to_wavs(mags_pageable, WIN, HOP, NFFT, GL_ITERS, seed=1234)
 
     e2e_steps = max(1, min(args.steps, 5))
+    def alloc_counters():
+        st = torch.cuda.memory_stats(dev)
+        out = {'device_alloc': st.get('num_device_alloc', 0), 'device_free': st.get('num_device_free', 0)}
+        try:
+            hs = torch.cuda.host_memory_stats()
+            out['host_alloc'] = hs.get('num_host_alloc', 0)
+            out['host_free'] = hs.get('num_host_free', 0)
+        except Exception:
+            pass
+        return out
+
+    gl_e2e()
+    c0 = alloc_counters()
     gl_e2e_ms, gl_e2e_calls = timed_calls(gl_e2e, e2e_steps, max(1, args.warmup))
+    c1 = alloc_counters()
+    e2e_allocs = {k: c1[k] - c0[k] for k in c1}      # cudaMalloc / cudaHostAlloc calls inside the e2e loop
     gl_e2e_value = total_audio * e2e_steps / (gl_e2e_ms / 1000.0)
     gl_e2e_pg_ms = timed(gl_e2e_pageable, e2e_steps, max(1, args.warmup))
     h2d = total_frames * N_BINS * 4
@@ -410,7 +425,7 @@ def run_ours(args):
             'e2e': {'value': gl_e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': gl_e2e_ms / e2e_steps,
                     'inputs': 'pinned host numpy arrays (pkg.pinned_empty), outputs numpy in pinned memory',
-                    'per_call_ms_rank0': gl_e2e_calls,
+                    'per_call_ms_rank0': gl_e2e_calls, 'allocator_calls_in_loop': e2e_allocs,
                     'pageable_inputs_value': total_audio * e2e_steps / (gl_e2e_pg_ms / 1000.0)},
             'gpu_launches': args.steps * (GL_ITERS + 2),
             'roofline': {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',

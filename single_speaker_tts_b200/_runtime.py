@@ -237,7 +237,12 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
             ready = torch.cuda.Event()
             ready.record(main)
             compute[1].wait_event(ready)
-            flag_dev.record_stream(compute[1])
+        # Device tensors cross streams here (uploaded on one, consumed on another, downloaded on a third).
+        # Instead of record_stream -- which makes the caching allocator defer their reuse behind events
+        # and fall back to cudaMalloc in the next call -- every tensor is kept alive in `keep` until all
+        # streams have been synchronised at the end of the call: then freeing is hazard-free and the next
+        # call finds exactly the blocks it needs in the allocator's per-stream caches.
+        keep = [flag_dev]
         outs = []
         nxt = upload(0)
         for k, (i0, i1) in enumerate(ranges):
@@ -247,10 +252,6 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
             comp = compute[k % len(compute)]
             with torch.cuda.stream(comp):
                 comp.wait_event(ev)
-                # tensors allocated on the copy stream are consumed on the compute stream
-                mag_dev.record_stream(comp)
-                if phase_dev is not None:
-                    phase_dev.record_stream(comp)
                 if denormalize is not None:
                     ref_db, max_db, power = [float(v) for v in denormalize]
                     _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), tf * n_bins, ref_db, max_db, power,
@@ -275,9 +276,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                     done = torch.cuda.Event()
                     done.record(comp)
                     back.wait_event(done)
-                    wav_dev.record_stream(back)
-                    if mse_dev is not None:
-                        mse_dev.record_stream(back)
+                keep.append((mag_dev, phase_dev, ws, wav_dev, mse_dev))
             with torch.cuda.stream(back):
                 outs.append((_hostio.download(wav_dev), _hostio.download(mse_dev) if return_mse else None, so, fo))
             if k + 1 < len(ranges):
@@ -288,6 +287,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         main.synchronize()
         if piped:
             back.synchronize()
+            copy.synchronize()
+        del keep, nxt, mag_dev, phase_dev, ws, wav_dev, mse_dev
     _gl_plans.reap()
     if flag is not None and int(flag[0]) != 0:
         # same error as the reference's decibel_to_magnitude (audio/conversion.py:47-49)
@@ -321,6 +322,7 @@ class FeatureBatch:
         self.minmax = None    # (n_clips, 4) float64
         self.mel_basis = None
         self.trim_bounds = None  # (n_clips, 2) int64 (start, end) when trimming was requested
+        self._keep = None        # device tensors of a pipelined call, released after its final sync
 
     def rows(self, arr, i, padded=False):
         a, b = int(self.row_off[i]), int(self.row_off[i + 1])
@@ -380,7 +382,6 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
                 up = torch.cuda.Event()
                 up.record(_streams[0])
             main.wait_event(up)
-            wav_dev.record_stream(main)
         else:
             wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav')
         if trim is not None:
@@ -445,9 +446,9 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             done = torch.cuda.Event()
             done.record(main)
             back.wait_event(done)
-            for t in (spec_dev, lin_dev, mel_dev, raw_dev, mm_dev):
-                if t is not None:
-                    t.record_stream(back)
+            # kept alive until stft_features_parts has synchronised the streams (no record_stream: see
+            # griffin_lim_batch)
+            res._keep = (wav_dev, spec_dev, lin_dev, mel_dev, raw_dev, mm_dev)
         with torch.cuda.stream(back):
             res.spec = _hostio.download(spec_dev).view(np.complex64).reshape(rows, n_bins) if want_spec else None
             res.lin_db = _hostio.download(lin_dev) if want_lin else None
@@ -483,5 +484,8 @@ def stft_features_parts(wavs, *args, **kwargs):
             parts.append((i0, i1, stft_features_batch(wavs[i0:i1], *args, _streams=streams, _slot=k, **kwargs)))
         torch.cuda.current_stream().synchronize()
         streams[1].synchronize()
+        streams[0].synchronize()
+        for _, _, part in parts:
+            part._keep = None
     _feat_plans.reap()
     return parts

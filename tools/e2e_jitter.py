@@ -32,3 +32,36 @@ for i in range(30):
     del w
 print(' '.join('%.1f' % t for t in ts))
 print('median %.2f  min %.2f  max %.2f' % (np.median(ts), min(ts), max(ts)))
+
+# bench.py style: no device-wide synchronisation between calls, one event after every call
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(13)]
+ev[0].record()
+for i in range(12):
+    synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1234)
+    ev[i + 1].record()
+torch.cuda.synchronize()
+print('events, no sync between calls:', ' '.join('%.1f' % ev[i].elapsed_time(ev[i + 1]) for i in range(12)))
+import gc
+gc.disable()
+ev[0].record()
+for i in range(12):
+    synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1234)
+    ev[i + 1].record()
+torch.cuda.synchronize()
+print('same, gc disabled:', ' '.join('%.1f' % ev[i].elapsed_time(ev[i + 1]) for i in range(12)))
+gc.enable()
+big = [torch.empty(600_000_000, dtype=torch.uint8, device='cuda') for _ in range(4)]   # bench holds ~2.4 GB of device buffers
+ev[0].record()
+for i in range(12):
+    synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1234)
+    ev[i + 1].record()
+torch.cuda.synchronize()
+print('with 2.4 GB held:', ' '.join('%.1f' % ev[i].elapsed_time(ev[i + 1]) for i in range(12)))
+import time
+for i in range(6):
+    t0 = time.perf_counter()
+    w = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1234)
+    t1 = time.perf_counter()
+    del w
+    t2 = time.perf_counter()
+    print('call %.1f ms, dropping the result %.1f ms' % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
