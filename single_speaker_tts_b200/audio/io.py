@@ -5,8 +5,12 @@ The reference goes through ``librosa.load(sr=None)`` / ``librosa.output.write_wa
 (audio/io.py:30,53); here PCM wav files are read and written with ``scipy.io.wavfile`` with the
 same conventions (float32 in [-1, 1), mono mix-down, native sampling rate).
 """
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 from scipy.io import wavfile
+
+_IO_THREADS = 8
 
 
 def load_wav(wav_path, offset=0.0, duration=None):
@@ -33,3 +37,48 @@ def save_wav(wav_path, wav, sampling_rate, norm=False):
     if norm and wav.size and np.max(np.abs(wav)) > 0:
         wav = wav / np.max(np.abs(wav))
     wavfile.write(wav_path, int(sampling_rate), wav.astype(np.float32))
+
+
+def load_wavs(paths, threads=_IO_THREADS):
+    """Decode a list of wav files with a few threads (file reads and the int16 -> float32 conversion
+    release the GIL); same result, same order as ``[load_wav(p) for p in paths]``."""
+    paths = list(paths)
+    if len(paths) < 2 or threads < 2:
+        return [load_wav(p) for p in paths]
+    with ThreadPoolExecutor(max_workers=min(threads, len(paths))) as ex:
+        return list(ex.map(load_wav, paths))
+
+
+def prefetch_batches(paths, batch, threads=_IO_THREADS):
+    """Yield ``(paths[s:s + batch], load_wavs(...))`` with the NEXT batch being decoded in the
+    background while the caller works on the current one (the device calls block the caller's
+    thread only until their final synchronisation)."""
+    paths = list(paths)
+    starts = list(range(0, len(paths), batch))
+    if not starts:
+        return
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        fut = ex.submit(load_wavs, paths[0:batch], threads)
+        for i, s in enumerate(starts):
+            cur = fut.result()
+            if i + 1 < len(starts):
+                n = starts[i + 1]
+                fut = ex.submit(load_wavs, paths[n:n + batch], threads)
+            yield paths[s:s + batch], cur
+
+
+def save_npz_many(items, threads=_IO_THREADS):
+    """Write ``(path, {key: array})`` pairs with ``np.savez`` from a few threads (uncompressed zip:
+    byte-compatible with the reference's files, datasets/dataset_helper.py:355)."""
+    items = list(items)
+
+    def write(item):
+        path, arrays = item
+        np.savez(path, **arrays)
+
+    if len(items) < 2 or threads < 2:
+        for it in items:
+            write(it)
+        return
+    with ThreadPoolExecutor(max_workers=min(threads, len(items))) as ex:
+        list(ex.map(write, items))

@@ -11,7 +11,7 @@ import numpy as np
 
 from ..audio.conversion import ms_to_samples
 from ..audio.features import features_batch
-from ..audio.io import load_wav
+from ..audio.io import load_wav, prefetch_batches, save_npz_many
 from ..params import model_params
 
 
@@ -62,14 +62,16 @@ class DatasetHelper:
         keys ``mel_mag_db`` / ``linear_mag_db``; clips go to the device in batches."""
         n_samples = len(paths)
         print('Loaded {} dataset entries.'.format(n_samples))
-        for s in range(0, n_samples, batch_clips):
-            chunk = paths[s:s + batch_clips]
-            wavs, srs = zip(*[load_wav(p) for p in chunk])
+        # decode of batch k + 1 (threads) overlaps the device work and the .npz writes of batch k
+        for chunk, loaded in prefetch_batches(paths, batch_clips):
+            wavs, srs = zip(*loaded)
             feats = cls.features_from_wavs(list(wavs), sampling_rate=srs[0])
+            items = []
             for wav_path, (mel_mag_db, linear_mag_db) in zip(chunk, feats):
                 out_path = '{}.npz'.format(os.path.splitext(wav_path)[0])
                 print('Writing: "{}"'.format(out_path))
-                np.savez(out_path, mel_mag_db=mel_mag_db, linear_mag_db=linear_mag_db)
+                items.append((out_path, {'mel_mag_db': mel_mag_db, 'linear_mag_db': linear_mag_db}))
+            save_npz_many(items)
 
 
 class LJSpeechDatasetHelper(DatasetHelper):

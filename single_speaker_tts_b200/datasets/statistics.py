@@ -9,7 +9,7 @@ reference prints as ``mel_mag_ref_db`` etc.
 import numpy as np
 
 from .. import _runtime
-from ..audio.io import load_wav
+from ..audio.io import load_wav, prefetch_batches
 
 STATS_N_FFT = 1024
 STATS_HOP = STATS_N_FFT // 4
@@ -53,10 +53,9 @@ def collect_decibel_statistics_from_wavs(wavs, sampling_rate, batch_clips=512, p
 def collect_decibel_statistics(path_listing, batch_clips=512, precision='f64'):
     """reference datasets/statistics.py:69-98 -- average (min, max) dB over a list of wav files."""
     rows = []
-    for s in range(0, len(path_listing), batch_clips):
+    for _, loaded in prefetch_batches(path_listing, batch_clips):      # threaded decode, one batch ahead
         wavs, sr = [], None
-        for path in path_listing[s:s + batch_clips]:
-            wav, sr_i = load_wav(path)
+        for wav, sr_i in loaded:
             if sr is not None and sr_i != sr:
                 # mixed sampling rates: flush what we have, the filterbank depends on sr
                 rows.append(decibel_statistics_batch(wavs, sr, precision=precision))

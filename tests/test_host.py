@@ -185,3 +185,31 @@ def test_threaded_packing_keeps_order_and_values():
             assert np.array_equal(out.numpy(), np.concatenate(arrays).astype(np.float32))
     finally:
         _hostio._CHUNK_BYTES = old
+
+
+def test_threaded_wav_decode_prefetch_and_npz_writer(tmp_path):
+    """audio/io.py helpers behind pre_compute_features / collect_decibel_statistics: same order and
+    values as the serial loop; .npz files readable with the reference's keys (tacotron/train.py:135-137)."""
+    from scipy.io import wavfile
+    from single_speaker_tts_b200.audio import io as aio
+    rng = np.random.default_rng(3)
+    paths = []
+    for i in range(7):
+        p = str(tmp_path / ('c%d.wav' % i))
+        wavfile.write(p, 22050, (rng.standard_normal(500 + 37 * i) * 3000).astype(np.int16))
+        paths.append(p)
+    serial = [aio.load_wav(p) for p in paths]
+    threaded = aio.load_wavs(paths, threads=4)
+    assert all(np.array_equal(a[0], b[0]) and a[1] == b[1] for a, b in zip(serial, threaded))
+    seen = []
+    for chunk, loaded in aio.prefetch_batches(paths, 3, threads=2):
+        assert len(chunk) == len(loaded)
+        seen.extend(zip(chunk, loaded))
+    assert [p for p, _ in seen] == paths
+    assert all(np.array_equal(w[0], s[0]) for (_, w), s in zip(seen, serial))
+    items = [(str(tmp_path / ('f%d.npz' % i)), {'mel_mag_db': np.full((3, 400), i, np.float32),
+                                                 'linear_mag_db': np.full((3, 5125), -i, np.float32)}) for i in range(5)]
+    aio.save_npz_many(items, threads=3)
+    for i, (p, _) in enumerate(items):
+        z = np.load(p)
+        assert z['mel_mag_db'].shape == (3, 400) and float(z['linear_mag_db'][0, 0]) == -i
