@@ -257,8 +257,11 @@ SSTTS_D float2 seeded_phasor(unsigned long long seed, long long index) {
 // bshift > 0: a shorter transform (n_fft = 2048 >> bshift) embedded in the 2048-point one -- only
 // every (1 << bshift)-th bin exists (srow / prow are indexed by k >> bshift), the others are forced
 // to zero, which makes the inverse transform periodic with period n_fft (its first period is used).
-template <typename T, bool FROM_PHASE, bool WANT_MSE>
-SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
+// OUT_BREV: the result is written to (ro, io) in BIT-REVERSED slots (what a decimation-in-time first
+// pass of the inverse transform takes), otherwise in natural slots.  Slot indices are compile-time, so
+// the permutation is only a renaming of registers; ro / io may not alias re / im.
+template <typename T, bool FROM_PHASE, bool WANT_MSE, bool OUT_BREV>
+SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)[32], const float* srow,
                            const float2* __restrict__ prow,
                            const typename cx_of<T>::type* s_w2k, int lane, double& mse_acc, int bshift = 0,
                            unsigned long long phase_seed = 0, long long phase_base = 0) {
@@ -266,6 +269,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
   const int partner = (32 - lane) & 31;
   const int bmask = (1 << bshift) - 1;
   const bool real_bin = (lane & bmask) == 0;   // k = lane + 32 k2 and 1024 - k share lane's residue
+  T prev_r = T(0), prev_i = T(0);              // 2 Z'[N-k] received in the previous pair step
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
     const int sl_mine = k2;
@@ -279,9 +283,9 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
     T ykr, yki, ynr, yni;
     if (!FROM_PHASE) {
       const T zr = re[sl_mine], zi = im[sl_mine];
-      T pr = __shfl_sync(0xffffffffu, re[sl_part], partner);
-      T pi = __shfl_sync(0xffffffffu, im[sl_part], partner);
-      if (lane == 0) { pr = re[sl_alt]; pi = im[sl_alt]; }
+      // lane 0 is its own partner and pairs slot k2 with slot 32 - k2: select the source, then shuffle
+      const T pr = __shfl_sync(0xffffffffu, lane == 0 ? re[sl_alt] : re[sl_part], partner);
+      const T pi = __shfl_sync(0xffffffffu, lane == 0 ? im[sl_alt] : im[sl_part], partner);
       const T er = zr + pr, ei = zi - pi;   // Zk + conj Zn
       const T dr = zr - pr, di = zi + pi;   // Zk - conj Zn
       const T wor = w.x * di + w.y * dr;    // w * (di - i dr)
@@ -317,14 +321,18 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
     const T znr = e2r + o2i, zni = o2r - e2i;   // 2 Z'[N-k]
     const T rr = __shfl_sync(0xffffffffu, znr, partner);
     const T ri = __shfl_sync(0xffffffffu, zni, partner);
-    re[sl_mine] = zkr; im[sl_mine] = zki;
-    if (lane == 0) {
-      if (k2 != 0) { re[sl_alt] = znr; im[sl_alt] = zni; }
-    } else {
-      re[sl_part] = rr; im[sl_part] = ri;
+    // slot 32 - k2 (k2 >= 1) takes the partner's value of the PREVIOUS step for lanes >= 1 and lane 0's
+    // own value of this step (lane 0's shuffle returns its own znr); slot 16 is completed below
+    ro[OUT_BREV ? brev5(sl_mine) : sl_mine] = zkr; io[OUT_BREV ? brev5(sl_mine) : sl_mine] = zki;
+    if (k2 != 0) {
+      ro[OUT_BREV ? brev5(sl_alt) : sl_alt] = lane == 0 ? rr : prev_r;
+      io[OUT_BREV ? brev5(sl_alt) : sl_alt] = lane == 0 ? ri : prev_i;
     }
+    prev_r = rr; prev_i = ri;
   }
-  // k = 512 (lane 0, slot 16): X = conj(Z), Z' = conj(Y).
+  // slot 16: lanes >= 1 take the partner's value of the last step; lane 0 holds k = 512 there
+  // (self-conjugate): X = conj(Z), Z' = conj(Y).
+  ro[OUT_BREV ? brev5(16) : 16] = prev_r; io[OUT_BREV ? brev5(16) : 16] = prev_i;
   if (lane == 0) {
     const int sl = 16;
     const T s = fabs((T)srow[(HALF / 2) >> bshift]);
@@ -340,7 +348,7 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], const float* srow,
       const float2 p = prow ? prow[(HALF / 2) >> bshift] : seeded_phasor(phase_seed, phase_base + ((HALF / 2) >> bshift));
       yr = s * (T)p.x; yi = s * (T)p.y;
     }
-    re[sl] = T(2) * yr; im[sl] = T(-2) * yi;
+    ro[OUT_BREV ? brev5(sl) : sl] = T(2) * yr; io[OUT_BREV ? brev5(sl) : sl] = T(-2) * yi;
   }
 }
 
@@ -362,6 +370,9 @@ template <typename T> struct GLSmem {
   }
 };
 
+#ifndef SSTTS_CORE_BREV_OUT
+#define SSTTS_CORE_BREV_OUT 1
+#endif
 // One Griffin-Lim step over all tiles.  FROM_PHASE = true is the initial synthesis from the
 // random phase (no analysis half).  W warps per CTA, one frame per warp, tiles of <= W frames.
 template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE>
@@ -559,14 +570,16 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         __syncwarp();
       }
       double mse_acc = 0.0;
-      gl_frame_core<T, FROM_PHASE, WANT_MSE>(re, im, srow, prow, s_w2k, lane, mse_acc, bshift, A.phase_seed,
-                                             A.phase_first + row * n_bins);
+      T ro[32], io[32];
+      gl_frame_core<T, FROM_PHASE, WANT_MSE, SSTTS_CORE_BREV_OUT != 0>(re, im, ro, io, srow, prow, s_w2k, lane, mse_acc,
+                                                                        bshift, A.phase_seed, A.phase_first + row * n_bins);
       if (WANT_MSE) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
         if (lane == 0) A.mse_frame[row] = mse_acc;
       }
-      warp_fft1024<T, true, false, true>(re, im, plane, s_tw, lane);
+      // inverse transform: with the core's output in bit-reversed slots both passes are FMA-fused DIT
+      warp_fft1024<T, true, SSTTS_CORE_BREV_OUT != 0, true>(ro, io, plane, s_tw, lane);
       // windowed output frame into the (now dead) plane; slot index = m - mlo, zero outside
       // the window so that the pair store needs no per-element guard
 #pragma unroll
@@ -575,8 +588,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         const int i = m - lpad;
         if (m >= mlo && m < lpad + win + 1) {
           const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
-          const T v0 = re[n1] * w2.x;
-          const T v1 = im[n1] * w2.y;
+          const T v0 = ro[n1] * w2.x;
+          const T v1 = io[n1] * w2.y;
           typename cx_of<T>::type vv;
           vv.x = v0; vv.y = v1;
           *reinterpret_cast<typename cx_of<T>::type*>(plane + (m - mlo)) = vv;   // m - mlo is even
