@@ -23,6 +23,14 @@
 #pragma once
 #include "simt_compat.h"
 
+// 1: apply the inter-pass twiddles after the transpose, fused into the first butterfly stage of pass 2
+// (-32 instructions per transform).  Measured SLOWER on B200 (Griffin-Lim step 0.572 -> 0.579 ms, float32
+// features 0.43 -> 0.44 ms: the twiddle loads land behind the transpose loads on the critical path), so
+// the default keeps the separate twiddle loop before the transpose.
+#ifndef SSTTS_FUSE_TWIDDLE
+#define SSTTS_FUSE_TWIDDLE 0
+#endif
+
 namespace sstts {
 
 template <typename T> struct cx_of;
@@ -150,10 +158,40 @@ SSTTS_HD void dit_stage2_pruned(T (&re)[32], T (&im)[32]) {
   }
 }
 
+// First DIT stage (span 2, W = 1) fused with the inter-pass twiddles of the 1024-point transform:
+// slot 2g holds element e = brev5(2g) < 16 and slot 2g + 1 element e + 16; both are first multiplied by
+// their twiddle t_e = tw[32 e + lane] (conjugated for the inverse), then combined:
+//   A = x_e t_e,  out0 = A + x_(e+16) t_(e+16),  out1 = 2 A - out0
+// 10 instructions per butterfly instead of 8 (two twiddle multiplies) + 4 (butterfly).
+template <typename T, bool INV>
+SSTTS_D void dit_stage2_twiddled(T (&re)[32], T (&im)[32], const typename cx_of<T>::type* tw, int lane) {
+  typedef typename cx_of<T>::type C;
+#pragma unroll
+  for (int g = 0; g < 32; g += 2) {
+    const int e = brev5(g);
+    T ar = re[g], ai = im[g];
+    if (e != 0) {   // t_0 = 1
+      const C ta = tw[e * 32 + lane];
+      const T sy = INV ? -ta.y : ta.y;
+      const T tr = ar * ta.x - ai * sy, ti = ar * sy + ai * ta.x;
+      ar = tr; ai = ti;
+    }
+    const C tb = tw[(e + 16) * 32 + lane];
+    const T sb = INV ? -tb.y : tb.y;
+    const T br = re[g + 1], bi = im[g + 1];
+    const T sr = fma(br, tb.x, fma(-bi, sb, ar));
+    const T si = fma(br, sb, fma(bi, tb.x, ai));
+    re[g] = sr; im[g] = si;
+    re[g + 1] = fma(T(2), ar, -sr);
+    im[g + 1] = fma(T(2), ai, -si);
+  }
+}
+
 // In-register 32-point FFT.  DIT = false: element k in slot k -> result k in slot brev5(k).
 //                            DIT = true : element k in slot brev5(k) -> result k in slot k;
 //                            input elements outside [ZLO, ZHI] must be zero (default: none are).
-template <typename T, bool INV, bool DIT, int ZLO = 0, int ZHI = 31>
+// SKIP2: the span-2 stage has already been applied (dit_stage2_twiddled).
+template <typename T, bool INV, bool DIT, int ZLO = 0, int ZHI = 31, bool SKIP2 = false>
 SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
   if (!DIT) {
     dif_stage<T, INV, 32>(re, im);
@@ -162,7 +200,8 @@ SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
     dif_stage<T, INV, 4>(re, im);
     dif_stage<T, INV, 2>(re, im);
   } else {
-    if (ZLO > 0 || ZHI < 31) dit_stage2_pruned<T, ZLO, ZHI>(re, im);
+    if (SKIP2) {}
+    else if (ZLO > 0 || ZHI < 31) dit_stage2_pruned<T, ZLO, ZHI>(re, im);
     else dit_stage<T, INV, 2>(re, im);
     dit_stage<T, INV, 4>(re, im);
     dit_stage<T, INV, 8>(re, im);
@@ -191,13 +230,18 @@ SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], T* xp, const typename cx_of<
                           int lane) {
   typedef typename cx_of<T>::type C;
   fft32<T, INV, P1_DIT, (P1_DIT ? ZLO : 0), (P1_DIT ? ZHI : 31)>(re, im);
+  // The twiddles W^(k1 n2) are symmetric in (k1, n2): with a DIT second pass they are applied AFTER the
+  // transpose, fused into its first butterfly stage (tw[n2 * 32 + lane], same conflict-free table walk).
+  constexpr bool FUSE_TW = P2_DIT && (SSTTS_FUSE_TWIDDLE != 0);
+  if (!FUSE_TW) {
 #pragma unroll
-  for (int k1 = 1; k1 < 32; ++k1) {
-    const int p = P1_DIT ? k1 : brev5(k1);  // slot holding pass-1 result k1
-    const C w = tw[k1 * 32 + lane];
-    const T vr = re[p], vi = im[p];
-    if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
-    else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
+    for (int k1 = 1; k1 < 32; ++k1) {
+      const int p = P1_DIT ? k1 : brev5(k1);  // slot holding pass-1 result k1
+      const C w = tw[k1 * 32 + lane];
+      const T vr = re[p], vi = im[p];
+      if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
+      else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
+    }
   }
 #pragma unroll
   for (int k1 = 0; k1 < 32; ++k1) xp[k1 * XPITCH + lane] = re[P1_DIT ? k1 : brev5(k1)];
@@ -211,7 +255,12 @@ SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], T* xp, const typename cx_of<
 #pragma unroll
   for (int n2 = 0; n2 < 32; ++n2) im[P2_DIT ? brev5(n2) : n2] = xp[lane * XPITCH + n2];
   __syncwarp();
-  fft32<T, INV, P2_DIT>(re, im);
+  if (FUSE_TW) {
+    dit_stage2_twiddled<T, INV>(re, im, tw, lane);
+    fft32<T, INV, true, 0, 31, true>(re, im);
+  } else {
+    fft32<T, INV, P2_DIT>(re, im);
+  }
 }
 
 }  // namespace sstts
