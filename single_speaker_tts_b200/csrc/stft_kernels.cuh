@@ -404,8 +404,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT, inv_nfft);
   __syncthreads();
 
-  // Tile record, loaded one tile ahead (one independent 48-byte load hidden behind the transform
-  // of the current tile).
+  // Tile records are single independent 48-byte loads, issued two rounds ahead.
   struct TileCtx { int a, b, parity, n_frames; long long f0, poff; };
   auto load_ctx = [&](int t) {
     TileCtx c;
@@ -512,14 +511,17 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   };
 
   int tile = blockIdx.x;
-  TileCtx cur = {0, 0, 0, 0, 0, 0}, nxt = {0, 0, 0, 0, 0, 0};
+  // records of this round's tile, the next one and the one after: a record is loaded two rounds
+  // before its first use, so no warp ever waits for it
+  TileCtx cur = {0, 0, 0, 0, 0, 0}, nxt = {0, 0, 0, 0, 0, 0}, nxt2 = {0, 0, 0, 0, 0, 0};
   if (tile < A.n_tiles) cur = load_ctx(tile);
+  if (tile + (int)gridDim.x < A.n_tiles) nxt = load_ctx(tile + gridDim.x);
   if (!FROM_PHASE && tile < A.n_tiles) stage(cur);
   __syncthreads();
 
   while (tile < A.n_tiles) {
     const int next = tile + gridDim.x;
-    if (next < A.n_tiles) nxt = load_ctx(next);
+    if (next + (int)gridDim.x < A.n_tiles) nxt2 = load_ctx(next + gridDim.x);
     const long long f0 = cur.f0;
     const long long poff = cur.poff;
     const int a = cur.a, FT = cur.b - cur.a;
@@ -673,6 +675,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     __syncthreads();
     tile = next;
     cur = nxt;
+    nxt = nxt2;
   }
 }
 
