@@ -376,8 +376,8 @@ def run_ours(args):
             'ms_per_step': per_launch_ms,
             'roofline': {'bound': 'hbm', 'achieved': alg / (per_launch_ms / 1000.0) / 1e9, 'peak': peak_gbs,
                          'unit': 'GB/s', 'frac': alg / (per_launch_ms / 1000.0) / 1e9 / peak_gbs,
-                         'traffic': measured_traffic('stft_feature_kernel<%s, StaticGeom<1102, 275, 2048>, 8, 1>'
-                                                     % ('double' if prec == 'f64' else 'float'))},
+                         'traffic': measured_traffic('stft_feature_kernel<%s, StaticGeom<1102, 275, 2048>, %d, 1>'
+                                                     % (('double', 4) if prec == 'f64' else ('float', 8)))},
         }
         lib.sstts_feat_plan_destroy(fplan)
         del lin, mel, wav_in
