@@ -194,15 +194,6 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
   yi = xi * inv;
 }
 
-#ifndef SSTTS_COLUMN_GATHER
-#define SSTTS_COLUMN_GATHER 1   // measured: 0.673 -> 0.656 ms per Griffin-Lim iteration launch
-#endif
-#ifndef SSTTS_COLUMN_STAGE
-#define SSTTS_COLUMN_STAGE 0      // measured slower (0.694 ms): needs a second pass for hop > NT
-#endif
-#ifndef SSTTS_STAGE_BATCH
-#define SSTTS_STAGE_BATCH 1       // measured: 0.656 -> 0.632 ms per Griffin-Lim iteration launch
-#endif
 constexpr int MAX_OVERLAP = 5;  // frames covering one sample: ceil(win / hop) <= 5 (host_plan.h)
 constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
 
@@ -431,36 +422,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     // common case: no reflection inside the span and every sample covered by a full set of frames
     const bool plain = (span_lo >= cpad) && (span_lo + span - cpad <= L_out) && (a * hop >= win - hop) &&
                        ((a * hop + span - 1) / hop <= n_frames - 1);
-#if SSTTS_COLUMN_STAGE
-    if (plain) {
-      // column form: residue r = s mod hop (span_lo - lpad = a hop); the loads of a thread are
-      // independent and issued back to back
-      const T* own = pin_own + span_lo;
-      const T* oth = pin_oth + span_lo;
-      for (int r = tid; r < hop; r += NT) {
-        const T rw = s_rw[r];
-        T x[W + MAX_OVERLAP - 1];
-#pragma unroll
-        for (int q = 0; q < W + MAX_OVERLAP - 1; ++q) {
-          const int s = q * hop + r;
-          x[q] = s < span ? own[s] : T(0);
-        }
-#pragma unroll
-        for (int q = 0; q < W + MAX_OVERLAP - 1; ++q) {
-          const int s = q * hop + r;
-          if (s < span && (s < le || s >= rb)) x[q] += oth[s];
-        }
-#pragma unroll
-        for (int q = 0; q < W + MAX_OVERLAP - 1; ++q) {
-          const int s = q * hop + r;
-          if (s < span) s_yin[s] = x[q] * rw;
-        }
-      }
-#else
     if (plain) {
       const T* own = pin_own + span_lo;
       const T* oth = pin_oth + span_lo;
-#if SSTTS_STAGE_BATCH
       // all global loads of the thread first (independent, in flight together), then the stores;
       // residue of sample s: (span_lo - lpad + s) mod hop = s mod hop since span_lo - lpad = a hop
       constexpr int NS = W + MAX_OVERLAP - 1;
@@ -485,18 +449,6 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         if (s < le || s >= rb) v += oth[s];
         s_yin[s] = v * s_rw[s % hop];
       }
-#else
-      int r = tid % hop;                 // (span_lo - lpad + s) mod hop with span_lo - lpad = a * hop
-#pragma unroll 4
-      for (int s = tid; s < span; s += NT) {
-        T v = own[s];
-        if (s < le || s >= rb) v += oth[s];
-        s_yin[s] = v * s_rw[r];
-        r += NT;
-        if (r >= hop) r %= hop;
-      }
-#endif
-#endif
     } else {
       for (int s = tid; s < span; s += NT) {
         int q = span_lo + s - cpad;
@@ -601,7 +553,6 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     __syncthreads();
     // Gather overlap-add (ascending frame order, no atomics) straight to the parity buffer:
     // sample s = q * hop + r receives frame q - j at offset r + j * hop, j = jmax .. 0.
-#if SSTTS_COLUMN_GATHER
     // column form: a thread owns the samples s = q * hop + r of one residue r; every slot element
     // is read exactly once and all indices are compile-time
     {
@@ -649,28 +600,6 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         }
       }
     }
-#else
-    {
-      const int dl = lpad - mlo;
-      const int pe = L.plane_elems;
-      const int jmax = (win - 1) / hop;
-      T* dst = pout_own + span_lo;
-      int q = tid / hop, r = tid % hop;
-#pragma unroll 2
-      for (int s = tid; s < span; s += NT) {
-        T acc = T(0);
-#pragma unroll
-        for (int j = jmax; j >= 0; --j) {
-          const int f = q - j;
-          const int off = r + j * hop;
-          if (f >= 0 && f < FT && off < win) acc += s_planes[f * pe + off + dl];
-        }
-        dst[s] = acc;
-        r += NT;
-        if (r >= hop) { q += r / hop; r %= hop; }
-      }
-    }
-#endif
     if (!FROM_PHASE && next < A.n_tiles) stage(nxt);
     __syncthreads();
     tile = next;
