@@ -158,6 +158,14 @@ typedef struct sstts_feat_outputs {
 int sstts_stft_features(const sstts_feat_plan* plan, const float* wav_dev,
                         const sstts_feat_outputs* out, void* stream);
 
+/* Time-stretch glue -- the part of `librosa.core.phase_vocoder(stft, rate)` that audio/effects.py:77-80
+ * keeps (its magnitude): spec_dev is a (n_frames, n_bins) interleaved complex64 STFT, frame-major;
+ * mag_out_dev receives (sstts_stretch_frames(n_frames, rate), n_bins) float32 magnitudes, linearly
+ * interpolated at the fractional frame positions t * rate. */
+int64_t sstts_stretch_frames(int64_t n_frames, double rate);
+int sstts_stretch_magnitude(const float* spec_dev, int64_t n_frames, int n_bins, double rate,
+                            float* mag_out_dev, void* stream);
+
 /* Silence trimming -- replaces `librosa.effects.trim(wav)` as called by datasets/lj_speech.py:119
  * (top_db 60, frame_length 2048, hop_length 512; wrapper audio/effects.py:188-215).
  * clip_start_dev / clip_len_dev: int64[n_clips] on the device; bounds_dev: int64[n_clips * 2]

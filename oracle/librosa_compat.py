@@ -199,3 +199,25 @@ def trim(y, top_db=60, frame_length=2048, hop_length=512):
     else:
         start, end = 0, 0
     return y[start:end], np.asarray([start, end])
+
+
+def phase_vocoder(D, rate, hop_length=None):
+    """librosa.core.phase_vocoder (0.6.x) -- used by the reference at audio/effects.py:77.
+    D: (1 + n_fft/2, T) complex; returns (1 + n_fft/2, len(arange(0, T, rate))) of D's dtype."""
+    n_fft = 2 * (D.shape[0] - 1)
+    if hop_length is None:
+        hop_length = int(n_fft // 4)
+    time_steps = np.arange(0, D.shape[1], rate, dtype=np.float64)
+    d_stretch = np.zeros((D.shape[0], len(time_steps)), D.dtype, order='F')
+    phi_advance = np.linspace(0, np.pi * hop_length, D.shape[0])
+    phase_acc = np.angle(D[:, 0])
+    D = np.pad(D, [(0, 0), (0, 2)], mode='constant')
+    for (t, step) in enumerate(time_steps):
+        columns = D[:, int(step):int(step + 2)]
+        alpha = np.mod(step, 1.0)
+        mag = ((1.0 - alpha) * np.abs(columns[:, 0]) + alpha * np.abs(columns[:, 1]))
+        d_stretch[:, t] = mag * np.exp(1.j * phase_acc)
+        dphase = (np.angle(columns[:, 1]) - np.angle(columns[:, 0]) - phi_advance)
+        dphase = dphase - 2.0 * np.pi * np.round(dphase / (2.0 * np.pi))
+        phase_acc += phi_advance + dphase
+    return d_stretch

@@ -255,6 +255,19 @@ def reconstruction_error(wav, sampling_rate, n_iters, angles=None):
     return mse
 
 
+def time_stretch(wav, rate, angles=None):
+    """audio/effects.py:46-86: STFT (1024 / 256 / 1024) -> phase vocoder -> |.| -> 25 Griffin-Lim
+    iterations.  Only the magnitude of the stretched spectrogram is used (:80)."""
+    if rate <= 0.0:
+        raise ValueError('The fixed rate used to stretch the signal must be greater 0.')
+    n_fft = 1024
+    win_len = n_fft
+    hop_len = win_len // 4
+    stft = linear_scale_spectrogram(wav, n_fft, hop_len, win_len)
+    mag = np.abs(lc.phase_vocoder(stft, rate))
+    return spectrogram_to_wav(mag, win_len, hop_len, n_fft, 25, angles=angles, batched_fft=True)
+
+
 # ----------------------------------------------------------------------------------------------
 # tacotron/inference.py glue before Griffin-Lim
 # ----------------------------------------------------------------------------------------------

@@ -59,3 +59,60 @@ def trim_batch(wavs, top_db=60, frame_length=2048, hop_length=512):
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         bounds = bounds_dev.cpu().numpy()
     return [w[b[0]:b[1]] for w, b in zip(wavs, bounds)], bounds
+
+
+def time_stretch(wav, rate):
+    """reference audio/effects.py:46-86 -- time-stretch by ``rate`` (> 1: faster): STFT (n_fft = win =
+    1024, hop 256) -> phase vocoder -> magnitude -> 25 Griffin-Lim iterations (random initial phase
+    from numpy's global RNG, like ``spectrogram_to_wav``).  The reference keeps only the MAGNITUDE of
+    the stretched spectrogram (:80), i.e. the linear interpolation of |STFT| at the fractional frame
+    positions; STFT, interpolation (``sstts_stretch_magnitude``) and Griffin-Lim all run on the
+    device.  Returns float32 audio of about ``len(wav) / rate`` samples."""
+    import ctypes
+    import torch
+    from .. import _hostio, _lib, _runtime
+    from .synthesis import spectrogram_to_wav
+    if rate <= 0.0:
+        raise ValueError('The fixed rate used to stretch the signal must be greater 0.')
+    n_fft = 1024
+    win_len = n_fft
+    hop_len = win_len // 4
+    reconstr_iters = 25
+    lib = _lib.load()
+    dev = _runtime.require_cuda()
+    n_bins = 1 + n_fft // 2
+    with torch.cuda.device(dev):
+        res = _runtime.stft_features_batch([np.asarray(wav)], n_fft, hop_len, win_len, want_spec=True,
+                                           keep_on_device=True)
+        n_frames = res.frames[0]
+        n_out = int(lib.sstts_stretch_frames(n_frames, float(rate)))
+        spec = torch.view_as_real(res.spec[:n_frames].contiguous())
+        mag_dev = torch.empty((n_out, n_bins), dtype=torch.float32, device=dev)
+        _lib.check(lib.sstts_stretch_magnitude(ctypes.c_void_p(spec.data_ptr()), n_frames, n_bins, float(rate),
+                                               ctypes.c_void_p(mag_dev.data_ptr()),
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        mag = _hostio.download(mag_dev)
+        torch.cuda.current_stream().synchronize()
+    return spectrogram_to_wav(mag.T, win_len, hop_len, n_fft, reconstr_iters)
+
+
+def stretch_magnitude(stft, rate):
+    """``np.abs(librosa.core.phase_vocoder(stft, rate))`` for a host ``(bins, T)`` complex64 STFT
+    (device kernel; the building block of :func:`time_stretch`)."""
+    import ctypes
+    import torch
+    from .. import _hostio, _lib, _runtime
+    lib = _lib.load()
+    dev = _runtime.require_cuda()
+    stft = np.asarray(stft)
+    n_bins, n_frames = stft.shape
+    with torch.cuda.device(dev):
+        spec = torch.from_numpy(np.ascontiguousarray(stft.T.astype(np.complex64)).view(np.float32)).to(dev)
+        n_out = int(lib.sstts_stretch_frames(n_frames, float(rate)))
+        mag_dev = torch.empty((n_out, n_bins), dtype=torch.float32, device=dev)
+        _lib.check(lib.sstts_stretch_magnitude(ctypes.c_void_p(spec.data_ptr()), n_frames, n_bins, float(rate),
+                                               ctypes.c_void_p(mag_dev.data_ptr()),
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        mag = _hostio.download(mag_dev)
+        torch.cuda.current_stream().synchronize()
+    return mag.T

@@ -312,6 +312,27 @@ __global__ void denormalize_magnitude_kernel(const float* __restrict__ x, long l
   if (bad && flag) atomicOr(flag, 1);
 }
 
+// Magnitude half of librosa.core.phase_vocoder as audio/effects.py:77-80 uses it (the stretched
+// spectrogram's phase is discarded by the np.abs that follows): output frame t sits at input position
+// step = t * rate; |D| is interpolated linearly between frames floor(step) and floor(step) + 1 (frames
+// past the end count as zero, like the two zero columns librosa pads).
+__global__ void stretch_magnitude_kernel(const float2* __restrict__ spec, long long n_frames, int n_bins,
+                                         double rate, long long n_out, float* __restrict__ mag_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_out * n_bins; i += stride) {
+    const long long t = i / n_bins;
+    const int k = (int)(i - t * n_bins);
+    const double step = (double)t * rate;              // np.arange(0, T, rate)[t]
+    const long long c0 = (long long)step;
+    const double alpha = step - floor(step);           // np.mod(step, 1.0)
+    float m0 = 0.0f, m1 = 0.0f;
+    if (c0 < n_frames) { const float2 v = spec[c0 * n_bins + k]; m0 = hypotf(v.x, v.y); }
+    if (c0 + 1 < n_frames) { const float2 v = spec[(c0 + 1) * n_bins + k]; m1 = hypotf(v.x, v.y); }
+    mag_out[i] = (float)((1.0 - alpha) * (double)m0 + alpha * (double)m1);
+  }
+}
+
 __global__ void minmax_init_kernel(long long* mm, int n_clips) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_clips * 4) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
@@ -433,6 +454,28 @@ int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_
 
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
   return sstts_random_phase_at(seed, 0, n, phase_dev, stream);
+}
+
+int64_t sstts_stretch_frames(int64_t n_frames, double rate) {
+  if (n_frames < 1 || !(rate > 0.0)) return 0;
+  int64_t n = (int64_t)ceil((double)n_frames / rate);   // len(np.arange(0, n_frames, rate))
+  while (n > 0 && (double)(n - 1) * rate >= (double)n_frames) --n;
+  while ((double)n * rate < (double)n_frames) ++n;
+  return n;
+}
+
+int sstts_stretch_magnitude(const float* spec_dev, int64_t n_frames, int n_bins, double rate,
+                            float* mag_out_dev, void* stream) {
+  if (!spec_dev || !mag_out_dev || n_frames < 1 || n_bins < 1 || !(rate > 0.0))
+    return fail(SSTTS_ERR_INVALID, "bad stretch_magnitude arguments");
+  const long long n_out = sstts_stretch_frames(n_frames, rate);
+  long long blocks = (n_out * n_bins + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) return 0;
+  stretch_magnitude_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(spec_dev), n_frames, n_bins, rate, n_out, mag_out_dev);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int sstts_denormalize_magnitude(const float* norm_dev, int64_t n, double ref_db, double max_db,

@@ -429,3 +429,28 @@ def test_griffin_lim_n_fft_1024_time_stretch_geometry():
     r512 = ra.spectrogram_to_wav(np.abs(lc.stft(x, 512, 128, 512)), 512, 128, 512, 3,
                                  angles=np.exp(2j * np.pi * np.random.RandomState(2).rand(257, 1 + len(x) // 128)))
     assert rel_l2(w512, r512) < 1e-5
+
+
+def test_time_stretch_matches_the_reference_recipe():
+    """audio/effects.py:46-86: interpolated |STFT| (the part of the phase vocoder the reference keeps)
+    and the 25-iteration n_fft-1024 reconstruction, with the same numpy-seeded initial phase."""
+    from single_speaker_tts_b200.audio import effects
+    rng = np.random.default_rng(51)
+    x = speech_like_clip(256 * 50 + 33, rng)
+    S = lc.stft(x, 1024, 256, 1024)
+    for rate in (0.8, 1.0, 1.25, 2.3):
+        got = effects.stretch_magnitude(S, rate)
+        ref = np.abs(lc.phase_vocoder(S, rate))
+        assert got.shape == ref.shape and got.dtype == np.float32
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    for rate in (0.8, 1.25):
+        np.random.seed(3)
+        w = effects.time_stretch(x, rate)
+        T_out = len(np.arange(0, S.shape[1], rate))
+        np.random.seed(3)
+        ang = np.exp(2j * np.pi * np.random.rand(513, T_out))
+        ref = ra.time_stretch(x, rate, angles=ang)
+        assert w.shape == ref.shape == (256 * (T_out - 1),) and w.dtype == np.float32
+        assert rel_l2(w, ref) < GL_TOL
+    with pytest.raises(ValueError):
+        effects.time_stretch(x, 0.0)

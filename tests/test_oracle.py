@@ -165,3 +165,32 @@ def test_pavoque_recipe_restatement_shapes_and_floor():
     spec = np.zeros((5, 7)); spec[2, 3] = 1.0; spec[4, 5] = 1.0
     assert ra.silence_interval_from_spectrogram(spec, 0.5) == (3, 5)
     assert ra.silence_interval_from_spectrogram(spec, 2.0) is None
+
+
+def test_phase_vocoder_restatement():
+    """librosa.core.phase_vocoder (audio/effects.py:77): rate 1 reproduces the magnitudes and the frame
+    count; other rates interpolate |D| linearly at the fractional positions; a stationary sinusoid keeps
+    its bin and magnitude."""
+    from oracle import librosa_compat as lc
+    rng = np.random.default_rng(5)
+    D = (rng.standard_normal((513, 23)) + 1j * rng.standard_normal((513, 23))).astype(np.complex64)
+    same = lc.phase_vocoder(D, 1.0)
+    assert same.shape == D.shape and np.allclose(np.abs(same), np.abs(D), rtol=1e-6)
+    for rate in (0.5, 1.3, 2.0):
+        out = lc.phase_vocoder(D, rate)
+        steps = np.arange(0, D.shape[1], rate)
+        assert out.shape == (513, len(steps)) and out.dtype == np.complex64
+        Dp = np.pad(np.abs(D), [(0, 0), (0, 2)])
+        i0 = steps.astype(int)
+        a = steps - i0
+        assert np.allclose(np.abs(out), (1 - a) * Dp[:, i0] + a * Dp[:, i0 + 1], rtol=2e-6, atol=1e-6)
+    sr, f = 22050, 22050 * 40 / 1024.0
+    x = np.sin(2 * np.pi * f * np.arange(20000) / sr).astype(np.float32)
+    S = lc.stft(x, 1024, 256, 1024)
+    St = lc.phase_vocoder(S, 0.7)
+    mid = St[:, 10:-10]
+    assert np.all(np.argmax(np.abs(mid), axis=0) == 40)
+    # the phase of the peak bin advances by 2 pi f hop / sr per output frame (that is what the vocoder keeps)
+    dphi = np.angle(mid[40, 1:] / mid[40, :-1])
+    expect = np.angle(np.exp(1j * 2 * np.pi * f * 256 / sr))
+    assert np.abs(np.angle(np.exp(1j * (dphi - expect)))).max() < 1e-3
