@@ -158,6 +158,12 @@ typedef struct sstts_feat_outputs {
 int sstts_stft_features(const sstts_feat_plan* plan, const float* wav_dev,
                         const sstts_feat_outputs* out, void* stream);
 
+/* MFCCs of a mel spectrogram -- replaces `librosa.feature.mfcc(S=mel_spec, n_mfcc=...)` at
+ * audio/features.py:111: mel_dev (n_frames, n_mels) float64 frame-major -> out_dev (n_frames, n_mfcc)
+ * float64, the orthonormal DCT-II of every frame truncated to n_mfcc coefficients. */
+int sstts_dct_project(const double* mel_dev, int64_t n_frames, int n_mels, int n_mfcc, double* out_dev,
+                      void* stream);
+
 /* Time-stretch glue -- the part of `librosa.core.phase_vocoder(stft, rate)` that audio/effects.py:77-80
  * keeps (its magnitude): spec_dev is a (n_frames, n_bins) interleaved complex64 STFT, frame-major;
  * mag_out_dev receives (sstts_stretch_frames(n_frames, rate), n_bins) float32 magnitudes, linearly

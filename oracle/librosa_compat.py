@@ -221,3 +221,19 @@ def phase_vocoder(D, rate, hop_length=None):
         dphase = dphase - 2.0 * np.pi * np.round(dphase / (2.0 * np.pi))
         phase_acc += phi_advance + dphase
     return d_stretch
+
+
+def dct_filters(n_filters, n_input):
+    """librosa.filters.dct (0.6.x): orthonormal DCT-II basis, shape (n_filters, n_input)."""
+    basis = np.empty((n_filters, n_input))
+    basis[0, :] = 1.0 / np.sqrt(n_input)
+    samples = np.arange(1, 2 * n_input, 2) * np.pi / (2.0 * n_input)
+    for i in range(1, n_filters):
+        basis[i, :] = np.cos(i * samples) * np.sqrt(2.0 / n_input)
+    return basis
+
+
+def mfcc(S, n_mfcc=20):
+    """librosa.feature.mfcc(S=S, n_mfcc=n_mfcc) (0.6.x): ``np.dot(filters.dct(n_mfcc, S.shape[0]), S)``;
+    0.7 computes the same numbers with scipy.fftpack.dct(type=2, norm='ortho')."""
+    return np.dot(dct_filters(n_mfcc, S.shape[0]), S)

@@ -255,6 +255,11 @@ def reconstruction_error(wav, sampling_rate, n_iters, angles=None):
     return mse
 
 
+def calculate_mfccs(mel_spec, sampling_rate, n_mfcc):
+    """audio/features.py:89-113."""
+    return lc.mfcc(mel_spec, n_mfcc=n_mfcc)
+
+
 def time_stretch(wav, rate, angles=None):
     """audio/effects.py:46-86: STFT (1024 / 256 / 1024) -> phase vocoder -> |.| -> 25 Griffin-Lim
     iterations.  Only the magnitude of the stretched spectrogram is used (:80)."""

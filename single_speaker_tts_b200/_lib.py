@@ -60,6 +60,8 @@ SIGNATURES = {
                                           ctypes.c_void_p]),
     'sstts_random_phase_at': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_void_p]),
+    'sstts_dct_project': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
     'sstts_stretch_frames': (ctypes.c_int64, [ctypes.c_int64, ctypes.c_double]),
     'sstts_stretch_magnitude': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                                ctypes.c_void_p, ctypes.c_void_p]),

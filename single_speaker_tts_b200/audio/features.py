@@ -30,6 +30,30 @@ def mel_scale_spectrogram(wav, n_fft, sampling_rate, n_mels, fmin, fmax, hop_len
     return res.mel_raw.T
 
 
+def calculate_mfccs(mel_spec, sampling_rate, n_mfcc):
+    """Mel-frequency cepstral coefficients -- reference audio/features.py:89-113, i.e.
+    ``librosa.feature.mfcc(S=mel_spec, sr=sampling_rate, n_mfcc=n_mfcc)``: the orthonormal DCT-II
+    over the mel axis of a ``(n_mels, T)`` spectrogram.  Returns ``(n_mfcc, T)`` float64."""
+    import ctypes
+    import torch
+    from .. import _hostio, _lib
+    mel_spec = np.asarray(mel_spec)
+    if mel_spec.ndim != 2:
+        raise ValueError('mel_spec must have shape (n_mels, T)')
+    n_mels, n_frames = mel_spec.shape
+    lib = _lib.load()
+    dev = _runtime.require_cuda()
+    with torch.cuda.device(dev):
+        mel_dev = _hostio.upload_rows([mel_spec.T], n_mels, torch.float64, dev, slot='mfcc')
+        out_dev = torch.empty((n_frames, int(n_mfcc)), dtype=torch.float64, device=dev)
+        _lib.check(lib.sstts_dct_project(ctypes.c_void_p(mel_dev.data_ptr()), n_frames, n_mels, int(n_mfcc),
+                                         ctypes.c_void_p(out_dev.data_ptr()),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        out = _hostio.download(out_dev)
+        torch.cuda.current_stream().synchronize()
+    return out.T
+
+
 def features_batch(wavs, n_fft, hop_length, win_length, sampling_rate, n_mels, fmin, fmax,
                    linear_ref_db, linear_mag_max_db, mel_mag_ref_db, mel_mag_max_db, reduction=1,
                    precision='f64', trim=None):

@@ -333,6 +333,29 @@ __global__ void stretch_magnitude_kernel(const float2* __restrict__ spec, long l
   }
 }
 
+// librosa.feature.mfcc(S=mel_spec, n_mfcc) as called by audio/features.py:111: the orthonormal DCT-II
+// basis of librosa.filters.dct(n_mfcc, n_mels) applied along the mel axis, in float64 like np.dot.
+//   basis[0][m] = 1 / sqrt(n),  basis[c][m] = cos(c (2 m + 1) pi / (2 n)) sqrt(2 / n)
+__global__ void dct_project_kernel(const double* __restrict__ mel, long long n_frames, int n_mels, int n_mfcc,
+                                   double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double s0 = 1.0 / sqrt((double)n_mels), s1 = sqrt(2.0 / (double)n_mels);
+  for (; i < n_frames * n_mfcc; i += stride) {
+    const long long t = i / n_mfcc;
+    const int c = (int)(i - t * n_mfcc);
+    const double* row = mel + t * n_mels;
+    double acc = 0.0;
+    if (c == 0) {
+      for (int m = 0; m < n_mels; ++m) acc += s0 * row[m];
+    } else {
+      for (int m = 0; m < n_mels; ++m)
+        acc += (cospi((double)c * (double)(2 * m + 1) / (double)(2 * n_mels)) * s1) * row[m];
+    }
+    out[i] = acc;
+  }
+}
+
 __global__ void minmax_init_kernel(long long* mm, int n_clips) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_clips * 4) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
@@ -454,6 +477,18 @@ int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_
 
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
   return sstts_random_phase_at(seed, 0, n, phase_dev, stream);
+}
+
+int sstts_dct_project(const double* mel_dev, int64_t n_frames, int n_mels, int n_mfcc, double* out_dev,
+                      void* stream) {
+  if (!mel_dev || !out_dev || n_frames < 1 || n_mels < 1 || n_mfcc < 1 || n_mfcc > n_mels)
+    return fail(SSTTS_ERR_INVALID, "bad dct_project arguments (need 1 <= n_mfcc <= n_mels)");
+  long long blocks = (n_frames * n_mfcc + 127) / 128;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  dct_project_kernel<<<(int)blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mel_dev, n_frames, n_mels,
+                                                                                      n_mfcc, out_dev);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int64_t sstts_stretch_frames(int64_t n_frames, double rate) {

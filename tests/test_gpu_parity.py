@@ -454,3 +454,15 @@ def test_time_stretch_matches_the_reference_recipe():
         assert rel_l2(w, ref) < GL_TOL
     with pytest.raises(ValueError):
         effects.time_stretch(x, 0.0)
+
+
+def test_calculate_mfccs_matches_oracle():
+    rng = np.random.default_rng(61)
+    x = speech_like_clip(9000, rng)
+    mel = ra.mel_scale_spectrogram(x, NFFT, 22050, 80, 0, 8000, HOP, WIN, 1)
+    logmel = 10.0 * np.log10(np.maximum(1e-10, mel))
+    for n_mfcc in (13, 20, 80):
+        got = features.calculate_mfccs(logmel, 22050, n_mfcc)
+        ref = ra.calculate_mfccs(logmel, 22050, n_mfcc)
+        assert got.shape == ref.shape == (n_mfcc, mel.shape[1]) and got.dtype == np.float64
+        assert np.abs(got - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())

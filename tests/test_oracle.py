@@ -194,3 +194,10 @@ def test_phase_vocoder_restatement():
     dphi = np.angle(mid[40, 1:] / mid[40, :-1])
     expect = np.angle(np.exp(1j * 2 * np.pi * f * 256 / sr))
     assert np.abs(np.angle(np.exp(1j * (dphi - expect)))).max() < 1e-3
+
+
+def test_mfcc_restatement_equals_scipy_ortho_dct():
+    from scipy.fftpack import dct
+    from oracle import librosa_compat as lc
+    S = np.random.default_rng(8).standard_normal((80, 37))
+    assert np.allclose(lc.mfcc(S, 13), dct(S, axis=0, type=2, norm='ortho')[:13], atol=1e-12)
