@@ -68,7 +68,10 @@ int sstts_device_count(void);
 typedef struct sstts_gl_plan sstts_gl_plan;
 
 /* frame_off_host[n_utts + 1]: prefix sums of the per-utterance frame counts T_u (>= 1).
- * Utterance u produces hop_length * (T_u - 1) samples (librosa.istft centre trimming). */
+ * Utterance u produces hop_length * (T_u - 1) samples (librosa.istft centre trimming).
+ * Plans are created for the current device.  The configuration's tables (twiddles, window, mel
+ * filterbank) are cached per process; a plan owns only its offset / tile tables (one stream-ordered
+ * pool allocation).  Destroy a plan only after the work enqueued with it has completed. */
 int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t* frame_off_host,
                          sstts_gl_plan** plan_out);
 void sstts_gl_plan_destroy(sstts_gl_plan* plan);

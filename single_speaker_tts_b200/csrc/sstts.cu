@@ -10,8 +10,12 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "host_plan.h"
@@ -52,10 +56,6 @@ struct DeviceTables {
   void* tw1024 = nullptr;
   void* w2048 = nullptr;
   void* window = nullptr;
-  void release() {
-    cudaFree(tw1024); cudaFree(w2048); cudaFree(window);
-    tw1024 = w2048 = window = nullptr;
-  }
 };
 
 template <typename T>
@@ -82,6 +82,109 @@ StftTables<T> tables_view(const DeviceTables& D) {
   t.window = reinterpret_cast<const T*>(D.window);
   return t;
 }
+
+// Everything that depends only on the configuration -- transform tables, window, mel filterbank --
+// lives in a process-wide cache keyed by (device, precision, geometry, filterbank): a plan for a new
+// batch shape then costs one allocation and one copy (its offset / tile tables, packed into one blob)
+// instead of a dozen.  Entries are immutable and never freed (a few hundred KB per configuration).
+struct StaticTables {
+  DeviceTables tab;
+  MelCSR mel;
+  MelPadded melp;
+  std::vector<double> mel_dense;
+  int* d_mel_ptr = nullptr;
+  int* d_mel_k0 = nullptr;
+  void* d_mel_w = nullptr;
+  float* d_melp_w = nullptr;
+};
+typedef std::tuple<int, int, int, int, int, int, double, double> StaticKey;
+std::mutex g_static_mu;
+std::map<StaticKey, std::shared_ptr<StaticTables> > g_static;
+
+int get_static_tables(const sstts_stft_config* cfg, int device, bool with_mel, std::shared_ptr<StaticTables>* out) {
+  const bool f64 = cfg->precision == SSTTS_F64;
+  const int n_mels = with_mel ? cfg->n_mels : 0;
+  const double fmax = n_mels > 0 ? (cfg->mel_fmax > 0 ? cfg->mel_fmax : cfg->sampling_rate / 2.0) : 0.0;
+  const StaticKey key(device, cfg->precision, cfg->n_fft, cfg->win_length, n_mels > 0 ? cfg->sampling_rate : 0, n_mels,
+                      n_mels > 0 ? cfg->mel_fmin : 0.0, fmax);
+  std::lock_guard<std::mutex> lock(g_static_mu);
+  auto it = g_static.find(key);
+  if (it != g_static.end()) { *out = it->second; return 0; }
+  std::shared_ptr<StaticTables> S(new StaticTables());
+  int rc = f64 ? upload_tables<double>(cfg->win_length, S->tab) : upload_tables<float>(cfg->win_length, S->tab);
+  if (!rc && n_mels > 0) {
+    make_mel_csr(cfg->sampling_rate, cfg->n_fft, n_mels, cfg->mel_fmin, fmax, S->mel, &S->mel_dense);
+    make_mel_padded(S->mel, n_mels, FEAT_PLANE_ELEMS, S->melp);
+    rc = upload(S->mel.ptr, &S->d_mel_ptr);
+    if (!rc) rc = upload(S->mel.k0, &S->d_mel_k0);
+    if (!rc && S->melp.ok) rc = upload(S->melp.w, &S->d_melp_w);
+    if (!rc) {
+      if (f64) { double* d; rc = upload(S->mel.w, &d); S->d_mel_w = d; }
+      else { std::vector<float> wf(S->mel.w.begin(), S->mel.w.end()); float* d; rc = upload(wf, &d); S->d_mel_w = d; }
+    }
+  }
+  if (rc) return rc;     // partially filled entry is dropped (its few allocations leak only on a CUDA error)
+  g_static[key] = S;
+  *out = S;
+  return 0;
+}
+
+// One device allocation holding several host arrays back to back (256-byte aligned sections).
+struct DeviceBlob {
+  std::vector<char> host;
+  char* dev = nullptr;
+  template <typename T> size_t add(const std::vector<T>& v) {
+    const size_t off = (host.size() + 255) & ~(size_t)255;
+    host.resize(off + v.size() * sizeof(T));
+    if (!v.empty()) std::memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+  // Stream-ordered allocation from the device's default memory pool (kept warm: the release threshold
+  // is raised once) on a private non-blocking stream, so a plan for a new batch shape costs a few
+  // microseconds and never waits for the caller's streams -- a cudaMalloc / cudaMemcpy / cudaFree
+  // triple maps and unmaps memory and synchronises with the legacy default stream.  A plan must outlive
+  // the work that uses it (see sstts.h).
+  static cudaStream_t plan_stream(int device) {
+    static std::mutex mu;
+    static std::map<int, cudaStream_t> streams;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = streams.find(device);
+    if (it != streams.end()) return it->second;
+    cudaStream_t st = nullptr;
+    cudaMemPool_t pool;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); st = nullptr; }
+    if (st && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    streams[device] = st;
+    return st;
+  }
+  int commit() {
+    if (host.empty()) return 0;
+    int device = 0;
+    CU(cudaGetDevice(&device));
+    stream = plan_stream(device);
+    if (stream && cudaMallocAsync((void**)&dev, host.size(), stream) == cudaSuccess) {
+      pooled = true;
+      CU(cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+    } else {
+      (void)cudaGetLastError();
+      CU(cudaMalloc((void**)&dev, host.size()));
+      CU(cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice));
+    }
+    std::vector<char>().swap(host);
+    return 0;
+  }
+  template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(dev + off); }
+  void release() {
+    if (dev) { if (pooled) cudaFreeAsync(dev, stream); else cudaFree(dev); }
+    dev = nullptr;
+  }
+  bool pooled = false;
+  cudaStream_t stream = nullptr;
+};
 
 int check_config(const sstts_stft_config* cfg, bool allow_embedded) {
   if (!cfg) return fail(SSTTS_ERR_INVALID, "config is NULL");
@@ -126,7 +229,8 @@ int configure_kernel(K kernel, int threads, size_t smem, int* blocks_per_sm) {
 struct sstts_gl_plan {
   sstts_stft_config cfg;
   GLPlanHost host;
-  DeviceTables tab;
+  std::shared_ptr<StaticTables> st;     // transform tables + window (shared, cached per configuration)
+  DeviceBlob blob;                      // offset tables + tile records of this batch shape
   long long* d_frame_off = nullptr;
   long long* d_pad_off = nullptr;
   long long* d_sample_off = nullptr;
@@ -138,19 +242,13 @@ struct sstts_gl_plan {
 struct sstts_feat_plan {
   sstts_stft_config cfg;
   FeatPlanHost host;
-  DeviceTables tab;
-  MelCSR mel;
-  MelPadded melp;
-  std::vector<double> mel_dense;
+  std::shared_ptr<StaticTables> st;     // transform tables, window, mel filterbank
+  DeviceBlob blob;
   long long* d_sample_off = nullptr;
   long long* d_sample_len = nullptr;
   long long* d_frame_off = nullptr;
   long long* d_row_off = nullptr;
   FeatTile* d_tiles = nullptr;
-  int* d_mel_ptr = nullptr;
-  int* d_mel_k0 = nullptr;
-  void* d_mel_w = nullptr;
-  float* d_melp_w = nullptr;
   int device = 0;
   int n_sms = 0;
 };
@@ -188,12 +286,16 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
   cudaError_t e = cudaGetDevice(&P->device);
   if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
   P->n_sms = sm_count();
-  rc = (cfg->precision == SSTTS_F64) ? upload_tables<double>(cfg->win_length, P->tab)
-                                     : upload_tables<float>(cfg->win_length, P->tab);
-  if (!rc) rc = upload(P->host.frame_off, &P->d_frame_off);
-  if (!rc) rc = upload(P->host.pad_off, &P->d_pad_off);
-  if (!rc) rc = upload(P->host.sample_off, &P->d_sample_off);
-  if (!rc) rc = upload(P->host.tiles, &P->d_tiles);
+  rc = get_static_tables(cfg, P->device, false, &P->st);
+  if (!rc) {
+    const size_t o0 = P->blob.add(P->host.frame_off), o1 = P->blob.add(P->host.pad_off);
+    const size_t o2 = P->blob.add(P->host.sample_off), o3 = P->blob.add(P->host.tiles);
+    rc = P->blob.commit();
+    if (!rc && P->blob.dev) {
+      P->d_frame_off = P->blob.at<long long>(o0); P->d_pad_off = P->blob.at<long long>(o1);
+      P->d_sample_off = P->blob.at<long long>(o2); P->d_tiles = P->blob.at<GLTile>(o3);
+    }
+  }
   if (rc) { sstts_gl_plan_destroy(P); return rc; }
   *plan_out = P;
   return 0;
@@ -201,8 +303,7 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
 
 void sstts_gl_plan_destroy(sstts_gl_plan* P) {
   if (!P) return;
-  P->tab.release();
-  cudaFree(P->d_frame_off); cudaFree(P->d_pad_off); cudaFree(P->d_sample_off); cudaFree(P->d_tiles);
+  P->blob.release();
   delete P;
 }
 
@@ -238,7 +339,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   A.pad_off = P->d_pad_off;
   A.tiles = P->d_tiles;
   A.n_tiles = (int)H.tiles.size();
-  A.tab = tables_view<T>(P->tab);
+  A.tab = tables_view<T>(P->st->tab);
   A.mse_frame = nullptr;
   A.win = H.win; A.hop = H.hop; A.span_max = H.span_max; A.n_fft = H.n_fft;
 
@@ -378,10 +479,11 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   A.sample_off = P->d_sample_off; A.sample_len = P->d_sample_len;
   A.frame_off = P->d_frame_off; A.row_off = P->d_row_off;
   A.tiles = P->d_tiles; A.n_tiles = (int)H.tiles.size();
-  A.tab = tables_view<T>(P->tab);
-  A.mel_ptr = P->d_mel_ptr; A.mel_k0 = P->d_mel_k0; A.mel_w = reinterpret_cast<const T*>(P->d_mel_w);
+  const StaticTables& S = *P->st;
+  A.tab = tables_view<T>(S.tab);
+  A.mel_ptr = S.d_mel_ptr; A.mel_k0 = S.d_mel_k0; A.mel_w = reinterpret_cast<const T*>(S.d_mel_w);
   A.n_mels = P->cfg.n_mels;
-  A.mel_nnz = (int)P->mel.w.size();
+  A.mel_nnz = (int)S.mel.w.size();
   A.spec_out = reinterpret_cast<float2*>(O->spec_dev);
   A.lin_out = O->lin_db_dev;
   A.mel_out = O->mel_db_dev;
@@ -399,14 +501,14 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   if (A.n_mels < 1) { A.mel_out = nullptr; A.melraw_out = nullptr; }
 
   // the pre-calculation configuration runs the fused dB-feature mode of the kernel
-  const bool fast = P->melp.ok && P->d_melp_w && A.n_fft == NFFT && A.lin_out && A.mel_out && !A.spec_out &&
+  const bool fast = S.melp.ok && S.d_melp_w && A.n_fft == NFFT && A.lin_out && A.mel_out && !A.spec_out &&
                     !A.melraw_out && !A.minmax_out && A.mel_power == 1.0f && !O->force_generic;
-  A.melp_w = P->d_melp_w;
-  A.melp_slots = fast ? P->melp.n_slots : 0;
-  A.melp_total = fast ? P->melp.total : 0;
-  for (int j = 0; j < 4; ++j) { A.melp_len[j] = P->melp.len[j]; A.melp_woff[j] = P->melp.woff[j]; A.melp_mbase[j] = P->melp.mbase[j]; }
+  A.melp_w = S.d_melp_w;
+  A.melp_slots = fast ? S.melp.n_slots : 0;
+  A.melp_total = fast ? S.melp.total : 0;
+  for (int j = 0; j < 4; ++j) { A.melp_len[j] = S.melp.len[j]; A.melp_woff[j] = S.melp.woff[j]; A.melp_mbase[j] = S.melp.mbase[j]; }
 
-  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max, P->cfg.n_mels, (int)P->mel.w.size(),
+  const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max, P->cfg.n_mels, (int)S.mel.w.size(),
                                                  A.melp_total);
   auto kernel = fast ? stft_feature_kernel<T, G, W, FeatMode::kDbFeatures>
                      : stft_feature_kernel<T, G, W, FeatMode::kGeneric>;
@@ -546,26 +648,19 @@ int sstts_feat_plan_create_ranges(const sstts_stft_config* cfg, int n_clips, con
   cudaError_t e = cudaGetDevice(&P->device);
   if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
   P->n_sms = sm_count();
-  const bool f64 = cfg->precision == SSTTS_F64;
-  rc = f64 ? upload_tables<double>(cfg->win_length, P->tab) : upload_tables<float>(cfg->win_length, P->tab);
-  if (!rc && cfg->n_mels > 0) {
-    if (cfg->sampling_rate < 1) { sstts_feat_plan_destroy(P); return fail(SSTTS_ERR_INVALID, "sampling_rate must be > 0"); }
-    const double fmax = cfg->mel_fmax > 0 ? cfg->mel_fmax : cfg->sampling_rate / 2.0;
-    make_mel_csr(cfg->sampling_rate, cfg->n_fft, cfg->n_mels, cfg->mel_fmin, fmax, P->mel, &P->mel_dense);
-    make_mel_padded(P->mel, cfg->n_mels, FEAT_PLANE_ELEMS, P->melp);
-    rc = upload(P->mel.ptr, &P->d_mel_ptr);
-    if (!rc) rc = upload(P->mel.k0, &P->d_mel_k0);
-    if (!rc && P->melp.ok) rc = upload(P->melp.w, &P->d_melp_w);
-    if (!rc) {
-      if (f64) { double* d; rc = upload(P->mel.w, &d); P->d_mel_w = d; }
-      else { std::vector<float> wf(P->mel.w.begin(), P->mel.w.end()); float* d; rc = upload(wf, &d); P->d_mel_w = d; }
+  if (cfg->n_mels > 0 && cfg->sampling_rate < 1) { sstts_feat_plan_destroy(P); return fail(SSTTS_ERR_INVALID, "sampling_rate must be > 0"); }
+  rc = get_static_tables(cfg, P->device, cfg->n_mels > 0, &P->st);
+  if (!rc) {
+    const size_t o0 = P->blob.add(P->host.sample_off), o1 = P->blob.add(P->host.sample_len);
+    const size_t o2 = P->blob.add(P->host.frame_off), o3 = P->blob.add(P->host.row_off);
+    const size_t o4 = P->blob.add(P->host.tiles);
+    rc = P->blob.commit();
+    if (!rc && P->blob.dev) {
+      P->d_sample_off = P->blob.at<long long>(o0); P->d_sample_len = P->blob.at<long long>(o1);
+      P->d_frame_off = P->blob.at<long long>(o2); P->d_row_off = P->blob.at<long long>(o3);
+      P->d_tiles = P->blob.at<FeatTile>(o4);
     }
   }
-  if (!rc) rc = upload(P->host.sample_off, &P->d_sample_off);
-  if (!rc) rc = upload(P->host.sample_len, &P->d_sample_len);
-  if (!rc) rc = upload(P->host.frame_off, &P->d_frame_off);
-  if (!rc) rc = upload(P->host.row_off, &P->d_row_off);
-  if (!rc) rc = upload(P->host.tiles, &P->d_tiles);
   if (rc) { sstts_feat_plan_destroy(P); return rc; }
   *plan_out = P;
   return 0;
@@ -596,10 +691,7 @@ int sstts_trim_bounds(const float* wav_dev, int n_clips, const int64_t* clip_sta
 
 void sstts_feat_plan_destroy(sstts_feat_plan* P) {
   if (!P) return;
-  P->tab.release();
-  cudaFree(P->d_sample_off); cudaFree(P->d_sample_len); cudaFree(P->d_frame_off); cudaFree(P->d_row_off);
-  cudaFree(P->d_tiles);
-  cudaFree(P->d_mel_ptr); cudaFree(P->d_mel_k0); cudaFree(P->d_mel_w); cudaFree(P->d_melp_w);
+  P->blob.release();
   delete P;
 }
 
@@ -612,7 +704,7 @@ const int64_t* sstts_feat_row_offsets(const sstts_feat_plan* P) {
   return P ? reinterpret_cast<const int64_t*>(P->host.row_off.data()) : nullptr;
 }
 const double* sstts_feat_mel_basis(const sstts_feat_plan* P) {
-  return (P && !P->mel_dense.empty()) ? P->mel_dense.data() : nullptr;
+  return (P && P->st && !P->st->mel_dense.empty()) ? P->st->mel_dense.data() : nullptr;
 }
 
 int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const sstts_feat_outputs* out,
