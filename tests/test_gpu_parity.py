@@ -466,3 +466,32 @@ def test_calculate_mfccs_matches_oracle():
         ref = ra.calculate_mfccs(logmel, 22050, n_mfcc)
         assert got.shape == ref.shape == (n_mfcc, mel.shape[1]) and got.dtype == np.float64
         assert np.abs(got - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+
+
+def test_concurrent_callers_get_the_serial_results():
+    """tacotron/serve.py:69-72 calls the per-item function from a ThreadPool(6), the TF input pipeline
+    calls load_audio from >= 4 queue-runner threads (tacotron/params/training.py:14): the library and the
+    host runtime must be re-entrant (locked plan / table caches, thread-local staging and streams)."""
+    from concurrent.futures import ThreadPoolExecutor
+    mags, angs = _case([30, 12, 55, 9, 41, 23])
+    rng = np.random.default_rng(71)
+    clips = [speech_like_clip(int(n), rng) for n in (5000, 9000, 7000, 12000, 3000, 8000)]
+
+    def synth(i):
+        return synthesis.spectrogram_to_wav(mags[i], WIN, HOP, NFFT, 4, angles=angs[i])
+
+    def feats(i):
+        return LJSpeechDatasetHelper.features_from_wavs([clips[i]], sampling_rate=22050)[0]
+
+    serial_w = [synth(i) for i in range(6)]
+    serial_f = [feats(i) for i in range(6)]
+    for _ in range(3):
+        with ThreadPoolExecutor(max_workers=6) as ex:
+            fw = [ex.submit(synth, i) for i in range(6)]
+            ff = [ex.submit(feats, i) for i in range(6)]
+            got_w = [f.result() for f in fw]
+            got_f = [f.result() for f in ff]
+        for a, b in zip(serial_w, got_w):
+            assert np.array_equal(a, b)
+        for (m0, l0), (m1, l1) in zip(serial_f, got_f):
+            assert np.array_equal(m0, m1) and np.array_equal(l0, l1)
