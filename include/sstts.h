@@ -161,6 +161,10 @@ typedef struct sstts_feat_outputs {
 int sstts_stft_features(const sstts_feat_plan* plan, const float* wav_dev,
                         const sstts_feat_outputs* out, void* stream);
 
+/* 16-bit PCM decode -- the sample conversion of `load_wav` (audio/io.py:5-30, int16 / 32768 -> float32)
+ * on the device, so clips can be uploaded as 2-byte samples. */
+int sstts_pcm16_to_float(const int16_t* pcm_dev, int64_t n, float* out_dev, void* stream);
+
 /* MFCCs of a mel spectrogram -- replaces `librosa.feature.mfcc(S=mel_spec, n_mfcc=...)` at
  * audio/features.py:111: mel_dev (n_frames, n_mels) float64 frame-major -> out_dev (n_frames, n_mfcc)
  * float64, the orthonormal DCT-II of every frame truncated to n_mfcc coefficients. */

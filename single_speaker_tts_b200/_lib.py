@@ -60,6 +60,7 @@ SIGNATURES = {
                                           ctypes.c_void_p]),
     'sstts_random_phase_at': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_void_p]),
+    'sstts_pcm16_to_float': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     'sstts_dct_project': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]),
     'sstts_stretch_frames': (ctypes.c_int64, [ctypes.c_int64, ctypes.c_double]),

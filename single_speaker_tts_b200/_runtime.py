@@ -360,6 +360,11 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     if hop_length is None:
         hop_length = int(win_length // 4)
     lens = []
+    # clips may be handed over as raw 16-bit PCM (all of them): uploaded as 2-byte samples and converted
+    # on the device exactly like load_wav does on the host (int16 / 32768)
+    pcm16 = all(getattr(w, 'dtype', None) == np.int16 for w in wavs)
+    if not pcm16 and any(getattr(w, 'dtype', None) == np.int16 for w in wavs):
+        wavs = [(w.astype(np.float32) / 32768.0) if w.dtype == np.int16 else w for w in wavs]   # mixed list
     for w in wavs:
         if w.ndim != 1:
             raise ValueError('Invalid shape for monophonic audio: ndim={:d}'.format(w.ndim))
@@ -378,12 +383,18 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
         main = torch.cuda.current_stream()
         if _streams is not None:
             with torch.cuda.stream(_streams[0]):
-                wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav%d' % (_slot & 1))
+                wav_dev = _hostio.upload_flat(wavs, torch.int16 if pcm16 else torch.float32, dev,
+                                              slot='wav%d' % (_slot & 1))
                 up = torch.cuda.Event()
                 up.record(_streams[0])
             main.wait_event(up)
         else:
-            wav_dev = _hostio.upload_flat(wavs, torch.float32, dev, slot='wav')
+            wav_dev = _hostio.upload_flat(wavs, torch.int16 if pcm16 else torch.float32, dev, slot='wav')
+        pcm_dev = None
+        if pcm16:
+            pcm_dev = wav_dev                # kept alive until the conversion has run
+            wav_dev = torch.empty(pcm_dev.shape, dtype=torch.float32, device=dev)
+            _lib.check(lib.sstts_pcm16_to_float(_ptr(pcm_dev), int(sample_off[-1]), _ptr(wav_dev), _stream_ptr()))
         if trim is not None:
             top_db, t_frame, t_hop = trim
             start_dev = torch.from_numpy(clip_start).to(dev)
@@ -448,7 +459,7 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             back.wait_event(done)
             # kept alive until stft_features_parts has synchronised the streams (no record_stream: see
             # griffin_lim_batch)
-            res._keep = (wav_dev, spec_dev, lin_dev, mel_dev, raw_dev, mm_dev)
+            res._keep = (wav_dev, pcm_dev, spec_dev, lin_dev, mel_dev, raw_dev, mm_dev)
         with torch.cuda.stream(back):
             res.spec = _hostio.download(spec_dev).view(np.complex64).reshape(rows, n_bins) if want_spec else None
             res.lin_db = _hostio.download(lin_dev) if want_lin else None

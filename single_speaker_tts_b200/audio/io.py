@@ -31,6 +31,16 @@ def load_wav(wav_path, offset=0.0, duration=None):
     return np.ascontiguousarray(wav[start:end]), sr
 
 
+def load_wav_pcm16(wav_path):
+    """``(int16 mono samples, sampling_rate)`` when the file holds 16-bit mono PCM (the LJSpeech format),
+    else the float32 result of :func:`load_wav`.  The batched feature calls accept int16 clips and do the
+    ``/ 32768`` conversion on the device (``sstts_pcm16_to_float``), which halves the upload."""
+    sr, data = wavfile.read(wav_path)
+    if data.dtype == np.int16 and data.ndim == 1:
+        return np.ascontiguousarray(data), sr
+    return load_wav(wav_path)
+
+
 def save_wav(wav_path, wav, sampling_rate, norm=False):
     """reference audio/io.py:33-53 -- float wav writer, optional peak normalisation."""
     wav = np.asarray(wav)
@@ -39,17 +49,23 @@ def save_wav(wav_path, wav, sampling_rate, norm=False):
     wavfile.write(wav_path, int(sampling_rate), wav.astype(np.float32))
 
 
-def load_wavs(paths, threads=_IO_THREADS):
+def load_wavs(paths, threads=_IO_THREADS, pcm16=False):
     """Decode a list of wav files with a few threads (file reads and the int16 -> float32 conversion
-    release the GIL); same result, same order as ``[load_wav(p) for p in paths]``."""
+    release the GIL); same result, same order as ``[load_wav(p) for p in paths]``.  ``pcm16=True`` keeps
+    16-bit mono files as int16 (:func:`load_wav_pcm16`) when EVERY file of the list is such a file."""
     paths = list(paths)
+    loader = load_wav_pcm16 if pcm16 else load_wav
     if len(paths) < 2 or threads < 2:
-        return [load_wav(p) for p in paths]
-    with ThreadPoolExecutor(max_workers=min(threads, len(paths))) as ex:
-        return list(ex.map(load_wav, paths))
+        out = [loader(p) for p in paths]
+    else:
+        with ThreadPoolExecutor(max_workers=min(threads, len(paths))) as ex:
+            out = list(ex.map(loader, paths))
+    if pcm16 and not all(w.dtype == np.int16 for w, _ in out):
+        out = [((w.astype(np.float32) / 32768.0) if w.dtype == np.int16 else w, sr) for w, sr in out]
+    return out
 
 
-def prefetch_batches(paths, batch, threads=_IO_THREADS):
+def prefetch_batches(paths, batch, threads=_IO_THREADS, pcm16=False):
     """Yield ``(paths[s:s + batch], load_wavs(...))`` with the NEXT batch being decoded in the
     background while the caller works on the current one (the device calls block the caller's
     thread only until their final synchronisation)."""
@@ -58,12 +74,12 @@ def prefetch_batches(paths, batch, threads=_IO_THREADS):
     if not starts:
         return
     with ThreadPoolExecutor(max_workers=1) as ex:
-        fut = ex.submit(load_wavs, paths[0:batch], threads)
+        fut = ex.submit(load_wavs, paths[0:batch], threads, pcm16)
         for i, s in enumerate(starts):
             cur = fut.result()
             if i + 1 < len(starts):
                 n = starts[i + 1]
-                fut = ex.submit(load_wavs, paths[n:n + batch], threads)
+                fut = ex.submit(load_wavs, paths[n:n + batch], threads, pcm16)
             yield paths[s:s + batch], cur
 
 

@@ -457,6 +457,14 @@ __global__ void dct_project_kernel(const double* __restrict__ mel, long long n_f
   }
 }
 
+// 16-bit PCM -> float32 in [-1, 1) exactly as the host decode does (audio/io.py:30 via librosa.load:
+// int16 / 32768): clips can be uploaded as they sit in the wav files, at half the bytes.
+__global__ void pcm16_to_float_kernel(const short* __restrict__ pcm, long long n, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)pcm[i] * (1.0f / 32768.0f);
+}
+
 __global__ void minmax_init_kernel(long long* mm, int n_clips) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_clips * 4) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
@@ -579,6 +587,17 @@ int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_
 
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
   return sstts_random_phase_at(seed, 0, n, phase_dev, stream);
+}
+
+int sstts_pcm16_to_float(const int16_t* pcm_dev, int64_t n, float* out_dev, void* stream) {
+  if (n < 0 || (n > 0 && (!pcm_dev || !out_dev))) return fail(SSTTS_ERR_INVALID, "bad pcm16_to_float arguments");
+  if (n == 0) return 0;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pcm16_to_float_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const short*>(pcm_dev), n, out_dev);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int sstts_dct_project(const double* mel_dev, int64_t n_frames, int n_mels, int n_mfcc, double* out_dev,

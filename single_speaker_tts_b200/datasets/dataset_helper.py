@@ -63,7 +63,8 @@ class DatasetHelper:
         n_samples = len(paths)
         print('Loaded {} dataset entries.'.format(n_samples))
         # decode of batch k + 1 (threads) overlaps the device work and the .npz writes of batch k
-        for chunk, loaded in prefetch_batches(paths, batch_clips):
+        # 16-bit mono files (LJSpeech) go to the device as int16 and are converted there
+        for chunk, loaded in prefetch_batches(paths, batch_clips, pcm16=True):
             wavs, srs = zip(*loaded)
             feats = cls.features_from_wavs(list(wavs), sampling_rate=srs[0])
             items = []

@@ -53,7 +53,7 @@ def collect_decibel_statistics_from_wavs(wavs, sampling_rate, batch_clips=512, p
 def collect_decibel_statistics(path_listing, batch_clips=512, precision='f64'):
     """reference datasets/statistics.py:69-98 -- average (min, max) dB over a list of wav files."""
     rows = []
-    for _, loaded in prefetch_batches(path_listing, batch_clips):      # threaded decode, one batch ahead
+    for _, loaded in prefetch_batches(path_listing, batch_clips, pcm16=True):   # threaded decode, one batch ahead
         wavs, sr = [], None
         for wav, sr_i in loaded:
             if sr is not None and sr_i != sr:

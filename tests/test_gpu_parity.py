@@ -495,3 +495,34 @@ def test_concurrent_callers_get_the_serial_results():
             assert np.array_equal(a, b)
         for (m0, l0), (m1, l1) in zip(serial_f, got_f):
             assert np.array_equal(m0, m1) and np.array_equal(l0, l1)
+
+
+def test_pcm16_clips_are_decoded_on_the_device(tmp_path):
+    """N2: int16 clips (the LJSpeech file format) are uploaded as 2-byte samples and converted on the
+    device exactly like load_wav converts them on the host -- identical features, with and without the
+    trim step, also for a mixed int16 / float32 list and through the file-level driver."""
+    from scipy.io import wavfile
+    from single_speaker_tts_b200.audio import io as aio
+    rng = np.random.default_rng(81)
+    pcm = [np.round(speech_like_clip(int(n), rng) * 30000).astype(np.int16) for n in (9000, 15000, 4000)]
+    flt = [p.astype(np.float32) / 32768.0 for p in pcm]
+    for trim_silence in (False, True):
+        a = LJSpeechDatasetHelper.features_from_wavs(pcm, 22050, trim_silence=trim_silence)
+        b = LJSpeechDatasetHelper.features_from_wavs(flt, 22050, trim_silence=trim_silence)
+        c = LJSpeechDatasetHelper.features_from_wavs([pcm[0], flt[1], pcm[2]], 22050, trim_silence=trim_silence)
+        for (m0, l0), (m1, l1), (m2, l2) in zip(a, b, c):
+            assert np.array_equal(m0, m1) and np.array_equal(l0, l1)
+            assert np.array_equal(m0, m2) and np.array_equal(l0, l2)
+    paths = []
+    for i, p in enumerate(pcm):
+        path = str(tmp_path / ('u%d.wav' % i))
+        wavfile.write(path, 22050, p)
+        paths.append(path)
+    assert aio.load_wav_pcm16(paths[0])[0].dtype == np.int16
+    LJSpeechDatasetHelper.pre_compute_features(paths)
+    for path, (mel, lin) in zip(paths, LJSpeechDatasetHelper.features_from_wavs(flt, 22050)):
+        z = np.load(path[:-4] + '.npz')
+        assert np.array_equal(z['mel_mag_db'], mel) and np.array_equal(z['linear_mag_db'], lin)
+    s1 = statistics.collect_decibel_statistics(paths)
+    s2 = statistics.collect_decibel_statistics_from_wavs(flt, 22050)
+    assert np.array_equal(s1, s2)
