@@ -101,6 +101,12 @@ int sstts_griffin_lim_seeded(const sstts_gl_plan* plan, const float* mag_dev, ui
                              int64_t first_element, int n_iter, void* workspace_dev, float* wav_out_dev,
                              double* mse_frame_dev, void* stream);
 
+/* Peak normalisation of every utterance of a Griffin-Lim result in place -- replaces the
+ * `librosa.util.normalize(wav, norm=np.inf)` of `save_wav(path, wav, sr, norm=True)`
+ * (audio/io.py:33-53; tacotron/inference.py:199): y / max|y| (true division), unchanged when the peak
+ * is below float32 tiny.  wav_dev is the wav_out_dev of sstts_griffin_lim for the same plan. */
+int sstts_peak_normalize(const sstts_gl_plan* plan, float* wav_dev, void* stream);
+
 /* Fill n unit phasors exp(2 pi i u), u ~ U[0, 1) from a counter-based generator keyed by seed
  * (batched extension: replaces the host-side np.random.rand of audio/synthesis.py:85). */
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream);

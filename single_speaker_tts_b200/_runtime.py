@@ -149,7 +149,7 @@ def _split_by_frames(frames, first, growth=1):
 
 
 def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
-                      precision='f32', return_mse=False, device=None, denormalize=None):
+                      precision='f32', return_mse=False, device=None, denormalize=None, normalize_peak=False):
     """Griffin-Lim for a ragged batch (reference: audio/synthesis.py:43-125, one call per item).
 
     mags   : list of (1 + n_fft/2, T_i) magnitude spectrograms (any float dtype / layout).
@@ -161,6 +161,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
              outputs in its own orientation ``(T_i, 1 + n_fft/2)`` and the glue of
              tacotron/inference.py:94-101,175 (inv_normalize_decibel -> decibel_to_magnitude ->
              ** power) runs fused on the device before the first iteration.
+    normalize_peak : divide every waveform by its peak on the device -- the ``norm=True`` of the
+             reference's ``save_wav`` (audio/io.py:33-53), which tacotron/inference.py:199 applies.
     Returns (list of float32 waveforms of length hop*(T_i-1), list of mse floats or None).
 
     Large batches are processed as a pipeline of sub-batches: while sub-batch k iterates on the
@@ -271,6 +273,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                                                             ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
                                                             int(frame_base[i0]) * n_bins, int(n_iter), _ptr(ws),
                                                             _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
+                if normalize_peak:
+                    _lib.check(lib.sstts_peak_normalize(plan.handle, _ptr(wav_dev), _stream_ptr()))
                 # results go back on their own stream so that the next iterations start at once
                 if piped:
                     done = torch.cuda.Event()

@@ -44,22 +44,24 @@ def spectrogram_to_wav(mag, win_length, hop_length, n_fft, n_iter, angles=None, 
 
 
 def spectrograms_to_wavs(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
-                         precision='f32', return_mse=False):
+                         precision='f32', return_mse=False, normalize_peak=False):
     """Batched Griffin-Lim over a ragged list of (1 + n_fft/2, T_i) magnitude spectrograms.
 
     One device call for the whole batch (utterances packed with an offsets table).  ``angles`` is
     an optional list of initial phasors (one per item); otherwise the phase is generated on the
     device from ``seed`` (None: one seed is drawn from numpy's global RNG).
+    ``normalize_peak`` divides every waveform by its peak on the device (the ``norm=True`` of the
+    reference's ``save_wav``, tacotron/inference.py:199).
     Returns a list of float32 waveforms (and the list of last-iteration mse values if requested).
     """
     wavs, mses = _runtime.griffin_lim_batch(list(mags), win_length, hop_length, n_fft, n_iter,
                                             angles=angles, seed=seed, precision=precision,
-                                            return_mse=return_mse)
+                                            return_mse=return_mse, normalize_peak=normalize_peak)
     return (wavs, mses) if return_mse else wavs
 
 
 def model_outputs_to_wavs(spectrograms, ref_db, max_db, magnitude_power, win_length, hop_length, n_fft,
-                          n_iter, seed=None, precision='f32'):
+                          n_iter, seed=None, precision='f32', normalize_peak=False):
     """Model output -> waveforms in one device call (extension; replaces
     tacotron/inference.py:92-101 + :170-188 and tacotron/serve.py:39-72).
 
@@ -73,5 +75,6 @@ def model_outputs_to_wavs(spectrograms, ref_db, max_db, magnitude_power, win_len
     specs = [np.asarray(s) for s in spectrograms]
     wavs, _ = _runtime.griffin_lim_batch(specs, win_length, hop_length, n_fft, n_iter, seed=seed,
                                          precision=precision,
-                                         denormalize=(ref_db, max_db, magnitude_power))
+                                         denormalize=(ref_db, max_db, magnitude_power),
+                                         normalize_peak=normalize_peak)
     return wavs

@@ -457,6 +457,36 @@ __global__ void dct_project_kernel(const double* __restrict__ mel, long long n_f
   }
 }
 
+// Peak normalisation of the reconstructed utterances -- librosa.util.normalize(y, norm=np.inf) as
+// save_wav(..., norm=True) applies it (audio/io.py:33-53, tacotron/inference.py:199): y / max|y|, left
+// alone when the peak is below float32 tiny.  One CTA per utterance and pass (grid-stride over utterances).
+__global__ void peak_normalize_kernel(float* __restrict__ wav, const long long* __restrict__ sample_off, int n_utts) {
+  __shared__ float s_red[8];
+  __shared__ float s_peak;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int u = blockIdx.x; u < n_utts; u += gridDim.x) {
+    float* y = wav + sample_off[u];
+    const long long n = sample_off[u + 1] - sample_off[u];
+    float m = 0.0f;
+    for (long long i = tid; i < n; i += blockDim.x) m = fmaxf(m, fabsf(y[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+      float p = 0.0f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) p = fmaxf(p, s_red[w]);
+      s_peak = p;
+    }
+    __syncthreads();
+    const float peak = s_peak;
+    if (peak >= 1.17549435e-38f) {
+      for (long long i = tid; i < n; i += blockDim.x) y[i] = y[i] / peak;   // true division, like numpy
+    }
+    __syncthreads();
+  }
+}
+
 // 16-bit PCM -> float32 in [-1, 1) exactly as the host decode does (audio/io.py:30 via librosa.load:
 // int16 / 32768): clips can be uploaded as they sit in the wav files, at half the bytes.
 __global__ void pcm16_to_float_kernel(const short* __restrict__ pcm, long long n, float* __restrict__ out) {
@@ -587,6 +617,16 @@ int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_
 
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream) {
   return sstts_random_phase_at(seed, 0, n, phase_dev, stream);
+}
+
+int sstts_peak_normalize(const sstts_gl_plan* P, float* wav_dev, void* stream) {
+  if (!P || (P->host.total_samples > 0 && !wav_dev)) return fail(SSTTS_ERR_INVALID, "bad peak_normalize arguments");
+  if (P->host.total_samples == 0) return 0;
+  int grid = P->host.n_utts < 148 * 4 ? P->host.n_utts : 148 * 4;
+  peak_normalize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wav_dev, P->d_sample_off,
+                                                                                   P->host.n_utts);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int sstts_pcm16_to_float(const int16_t* pcm_dev, int64_t n, float* out_dev, void* stream) {

@@ -526,3 +526,18 @@ def test_pcm16_clips_are_decoded_on_the_device(tmp_path):
     s1 = statistics.collect_decibel_statistics(paths)
     s2 = statistics.collect_decibel_statistics_from_wavs(flt, 22050)
     assert np.array_equal(s1, s2)
+
+
+def test_peak_normalisation_matches_save_wav_norm():
+    """save_wav(..., norm=True) (audio/io.py:33-53, used at tacotron/inference.py:199) divides by the
+    peak; the device version must give the same float32 values (true division), utterance by utterance,
+    also across sub-batches."""
+    mags, angs = _case([40, 9, 100, 17])
+    plain = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3, angles=angs)
+    normed = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 3, angles=angs, normalize_peak=True)
+    for w, n in zip(plain, normed):
+        ref = w / np.max(np.abs(w))
+        assert n.dtype == np.float32 and np.array_equal(n, ref.astype(np.float32))
+        assert abs(float(np.max(np.abs(n))) - 1.0) < 1e-6
+    z = synthesis.spectrograms_to_wavs([np.zeros((1025, 6), np.float32)], WIN, HOP, NFFT, 1, seed=1, normalize_peak=True)
+    assert np.array_equal(z[0], np.zeros(HOP * 5, np.float32))
