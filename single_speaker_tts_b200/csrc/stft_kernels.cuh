@@ -487,7 +487,14 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       const float2* prow = (FROM_PHASE && A.phase0) ? A.phase0 + row * n_bins : nullptr;
       const float* srow = mrow;
       T re[32], im[32];
-      if (!FROM_PHASE) {
+      if (FROM_PHASE) {
+        // the frame's |S| row goes through shared memory here too: one asynchronous copy and one wait
+        // instead of 33 dependent global loads inside the pair loop
+        const int mis = stage_row_async(s_mag, mrow, lane, n_bins);
+        sstts_cp_async_wait_all();
+        __syncwarp();
+        srow = s_mag + mis;
+      } else {
         const int mis = stage_row_async(s_mag, mrow, lane, n_bins);
         srow = s_mag + mis;
         const T* fin = s_yin + warp * hop - lpad;  // fin[m], m in [lpad, lpad + win)
