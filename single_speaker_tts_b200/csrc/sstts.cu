@@ -211,9 +211,22 @@ int sm_count() {
   return n;
 }
 
+// The dynamic shared memory limit of a kernel is process-wide state: concurrent callers with different
+// batch shapes (different tile spans) would race if each set "its" size, so every caller sets the same
+// value, the device's opt-in maximum; the occupancy query below uses the actual size.
+int max_optin_smem() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+  return v;
+}
+
 template <typename K>
 int configure_kernel(K kernel, int threads, size_t smem, int* blocks_per_sm) {
-  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int limit = max_optin_smem();
+  if (limit <= 0 || smem > (size_t)limit)
+    return fail(SSTTS_ERR_CUDA, "kernel does not fit on this device (shared memory)");
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
   if (occ < 1) return fail(SSTTS_ERR_CUDA, "kernel does not fit on this device (shared memory / registers)");

@@ -473,7 +473,7 @@ def test_concurrent_callers_get_the_serial_results():
     calls load_audio from >= 4 queue-runner threads (tacotron/params/training.py:14): the library and the
     host runtime must be re-entrant (locked plan / table caches, thread-local staging and streams)."""
     from concurrent.futures import ThreadPoolExecutor
-    mags, angs = _case([30, 12, 55, 9, 41, 23])
+    mags, angs = _case([30, 5, 55, 9, 41, 2])      # spans (hence dynamic shared memory sizes) differ per caller
     rng = np.random.default_rng(71)
     clips = [speech_like_clip(int(n), rng) for n in (5000, 9000, 7000, 12000, 3000, 8000)]
 
@@ -485,7 +485,7 @@ def test_concurrent_callers_get_the_serial_results():
 
     serial_w = [synth(i) for i in range(6)]
     serial_f = [feats(i) for i in range(6)]
-    for _ in range(3):
+    for _ in range(10):
         with ThreadPoolExecutor(max_workers=6) as ex:
             fw = [ex.submit(synth, i) for i in range(6)]
             ff = [ex.submit(feats, i) for i in range(6)]
