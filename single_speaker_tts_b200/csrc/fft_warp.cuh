@@ -9,11 +9,12 @@
 //     pass 2  32-point FFT over the register index again
 // Input and output use the same "element = 32 * slot + lane" indexing.  A 32-point pass is
 // either DIF (natural slot order in, bit-reversed out) or DIT (bit-reversed in, natural out).
-// Slot order is free wherever data comes from or goes to memory, so the kernels use DIT
-// (FMA-fused butterflies, zero-padding pruned for free) for three of the four passes of a
-// Griffin-Lim iteration and DIF only for the first inverse pass, which takes the forward
-// result in natural order straight from the registers: no register permutation is ever
-// executed, every slot index is a compile-time constant after unrolling.
+// Slot order is free wherever data comes from or goes to memory, and wherever the producer is
+// fully unrolled code (slot indices are then compile-time, so writing to slot brev5(k) instead of k
+// is only a renaming of registers): the kernels therefore use DIT (FMA-fused butterflies,
+// zero-padding pruned for free) for all four passes of a Griffin-Lim iteration -- the window load
+// and the conjugate-pair core hand their results over in bit-reversed slots.  The DIF stage is kept
+// for completeness and for the emulator's transform tests.  No register permutation is ever executed.
 // No 1/N scaling is applied here -- callers fold it into the synthesis window.
 //
 // The 32-point register FFT is radix-2 with the trivial twiddles (1, -i, (1-i)/sqrt2, ...)
