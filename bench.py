@@ -50,6 +50,16 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_ncu(kernel, key):
+    """One metric of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f)[kernel][key]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_traffic(kernel):
     """dram__bytes_read + dram__bytes_write per launch of `kernel` from the committed ncu
     --set full capture of this workload shape (profiles/r1_traffic.json), or None."""
@@ -431,6 +441,10 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                          'frac': gl_achieved / peak_gbs,
                          'traffic': measured_traffic('gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>'),
+                         'fp32_pipe_active_pct_ncu': measured_ncu('gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>',
+                                                                  'fp32_pipe_active_pct'),
+                         'issue_slots_active_pct_ncu': measured_ncu('gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>',
+                                                                    'issue_slots_active_pct'),
                          'kernel': 'gl_step_kernel',
                          'peak_source': peak_src, 'ms_per_launch': iter_ms,
                          'algorithmic_bytes_per_launch': gl_alg_bytes,

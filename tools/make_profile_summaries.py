@@ -43,14 +43,20 @@ rows = list(csv.reader(io.StringIO(raw)))
 h, units = rows[0], rows[1]
 kn, r_, w_, t_ = (h.index('Kernel Name'), h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum'),
                   h.index('gpu__time_duration.sum'))
+f_ = h.index('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')
+i_ = h.index('smsp__issue_active.avg.pct_of_peak_sustained_active')
+d_ = h.index('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')
 BY = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 US = {'ns': 1e-3, 'us': 1, 'ms': 1e3, 's': 1e6}
 agg = collections.OrderedDict()
 for r in rows[2:]:
     name = r[kn].replace('void ', '').replace('sstts::', '').split('(')[0]
-    agg.setdefault(name, []).append((float(r[r_]) * BY[units[r_]] + float(r[w_]) * BY[units[w_]], float(r[t_]) * US.get(units[t_], 1)))
+    agg.setdefault(name, []).append((float(r[r_]) * BY[units[r_]] + float(r[w_]) * BY[units[w_]], float(r[t_]) * US.get(units[t_], 1),
+                                     float(r[f_]), float(r[i_]), float(r[d_])))
 traffic = {k: {'dram_bytes_per_launch': sum(x[0] for x in v) / len(v), 'launches': len(v),
-               'gpu_time_us_under_ncu': sum(x[1] for x in v) / len(v)} for k, v in agg.items()}
+               'gpu_time_us_under_ncu': sum(x[1] for x in v) / len(v),
+               'fp32_pipe_active_pct': sum(x[2] for x in v) / len(v), 'issue_slots_active_pct': sum(x[3] for x in v) / len(v),
+               'dram_throughput_pct': sum(x[4] for x in v) / len(v)} for k, v in agg.items()}
 traffic['_source'] = ('ncu --set full --clock-control none -k regex:gl_step_kernel|stft_feature_kernel|gl_finalize|random_phase -c 20, '
                       'python tools/prof_run.py 3 (BASELINE configs[1]/[2] shapes: 256 clips, 112,916 frames, whole batch per '
                       'launch); profiles/%s_ncu_summary.txt' % tag)
