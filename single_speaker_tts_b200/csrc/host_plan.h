@@ -215,7 +215,9 @@ inline void make_mel_csr(int sr, int n_fft, int n_mels, double fmin, double fmax
 
 // The filterbank padded for the kernel's dB-feature mode: slot j holds the filters
 // m = mbase[j] + lane (top 32 filters first -- filter lengths grow with m, so a slot's filters have
-// similar lengths); w[woff[j] + 32 * i + lane] is element i of filter m, zero beyond its support.
+// similar lengths).  A filter is stored as PAIRS of weights starting at the even bin k0 & ~1:
+// pair i of filter m is (w[2 * (woff[j] + 32 * i + lane)], w[... + 1]) for bins (k0 & ~1) + 2 i and
+// + 2 i + 1, zero outside the filter's support; len / woff / total count pairs.
 // ok == false when the layout does not fit the kernel's limits (then the generic mode is used).
 struct MelPadded {
   int n_slots = 0, total = 0;
@@ -233,20 +235,24 @@ inline void make_mel_padded(const MelCSR& M, int n_mels, int mag_elems, MelPadde
     for (int l = 0; l < 32; ++l) {
       const int m = P.mbase[j] + l;
       if (m < 0 || m >= n_mels) continue;
-      const int n = M.ptr[m + 1] - M.ptr[m];
-      if (n > L) L = n;
+      const int n = M.ptr[m + 1] - M.ptr[m] + (M.k0[m] & 1);    // leading zero when k0 is odd
+      if ((n + 1) / 2 > L) L = (n + 1) / 2;
     }
     P.len[j] = L;
     P.woff[j] = P.total;
     P.total += 32 * L;
   }
-  P.w.assign((size_t)P.total, 0.0f);
+  P.w.assign((size_t)2 * P.total, 0.0f);
   for (int j = 0; j < P.n_slots; ++j)
     for (int l = 0; l < 32; ++l) {
       const int m = P.mbase[j] + l;
       if (m < 0 || m >= n_mels) continue;
-      if (M.k0[m] + P.len[j] > mag_elems) return;    // padded reads would leave the |S| plane
-      for (int i = M.ptr[m]; i < M.ptr[m + 1]; ++i) P.w[(size_t)P.woff[j] + 32 * (i - M.ptr[m]) + l] = (float)M.w[i];
+      const int k0e = M.k0[m] & ~1;
+      if (k0e + 2 * P.len[j] > mag_elems) return;    // padded reads would leave the |S| plane
+      for (int i = M.ptr[m]; i < M.ptr[m + 1]; ++i) {
+        const int e = (i - M.ptr[m]) + (M.k0[m] & 1);     // element index relative to the even start
+        P.w[2 * ((size_t)P.woff[j] + 32 * (e >> 1) + l) + (e & 1)] = (float)M.w[i];
+      }
     }
   P.ok = P.total > 0;
 }

@@ -685,8 +685,10 @@ template <typename T> struct FeatArgs {
   const T* mel_w;                 // [nnz]        filter weights (float64 -> T)
   int n_mels, mel_nnz;
   // the same filterbank padded for the fused dB-feature mode (FeatMode::kDbFeatures): slot j holds
-  // the filters m = melp_mbase[j] + lane (32 per slot, top filters first); element i of filter m is
-  // melp_w[melp_woff[j] + 32 * i + lane], zero beyond the filter's support, i < melp_len[j]
+  // the filters m = melp_mbase[j] + lane (32 per slot, top filters first).  Filters start at the even
+  // bin k0 & ~1 and are stored as PAIRS of weights: pair i of filter m is the float2
+  // melp_w[2 * (melp_woff[j] + 32 * i + lane)] covering bins (k0 & ~1) + 2 i, + 2 i + 1 (zero outside the
+  // filter's support), i < melp_len[j]; melp_total counts pairs.
   const float* melp_w;
   int melp_slots, melp_total;
   int melp_len[4], melp_woff[4], melp_mbase[4];
@@ -764,9 +766,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   int* s_mel_k0 = s_mel_ptr + round_up4(A.n_mels + 1);
   float* s_melp_w = reinterpret_cast<float*>(s_x + 2 * xbuf_elems);
   if (FAST) {
-    s_mel_k0 = reinterpret_cast<int*>(s_melp_w + round_up4(A.melp_total));
-    for (int i = tid; i < A.melp_total; i += NT) s_melp_w[i] = A.melp_w[i];
-    for (int i = tid; i < A.n_mels; i += NT) s_mel_k0[i] = A.mel_k0[i];
+    s_mel_k0 = reinterpret_cast<int*>(s_melp_w + round_up4(2 * A.melp_total));
+    for (int i = tid; i < 2 * A.melp_total; i += NT) s_melp_w[i] = A.melp_w[i];
+    for (int i = tid; i < A.n_mels; i += NT) s_mel_k0[i] = A.mel_k0[i] & ~1;   // even start of the pairs
   } else {
     for (int i = tid; i < A.mel_nnz; i += NT) s_mel_w[i] = A.mel_w[i];
     for (int i = tid; i < A.n_mels; i += NT) { s_mel_ptr[i] = A.mel_ptr[i]; s_mel_k0[i] = A.mel_k0[i]; }
@@ -936,17 +938,18 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
         for (int j = 0; j < A.melp_slots; ++j) {
           const int m = A.melp_mbase[j] + lane;
           const bool valid = m >= 0 && m < A.n_mels;
-          const float* wp = s_melp_w + A.melp_woff[j] + lane;
-          const float* mg = s_mag + (valid ? s_mel_k0[m] : 0);
+          // one 8-byte load of two weights and one of two magnitudes per step (the plane is 8-byte
+          // aligned and the pairs start at an even bin)
+          const float2* wp = reinterpret_cast<const float2*>(s_melp_w) + A.melp_woff[j] + lane;
+          const float2* mg = reinterpret_cast<const float2*>(s_mag + (valid ? s_mel_k0[m] : 0));
           const int len = A.melp_len[j];
           float acc0 = 0.0f, acc1 = 0.0f;
-          int i = 0;
 #pragma unroll 4
-          for (; i + 1 < len; i += 2) {
-            acc0 = fmaf(wp[32 * i], mg[i], acc0);
-            acc1 = fmaf(wp[32 * i + 32], mg[i + 1], acc1);
+          for (int i = 0; i < len; ++i) {
+            const float2 w = wp[32 * i], v = mg[i];
+            acc0 = fmaf(w.x, v.x, acc0);
+            acc1 = fmaf(w.y, v.y, acc1);
           }
-          if (i < len) acc0 = fmaf(wp[32 * i], mg[i], acc0);
           const float lm = sstts_log2_ftz(fmaxf(2e-5f, acc0 + acc1));
           if (valid) mel_row[m] = fminf(fmaxf(fmaf(lm, fm_a, fm_b), clip_lo), clip_hi);
         }
@@ -1013,12 +1016,12 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   }
 }
 
-// melp_total > 0 selects the dB-feature layout (padded float table + k0) instead of the CSR one.
+// melp_total > 0 (weight pairs) selects the dB-feature layout (padded float2 table + k0) instead of the CSR one.
 template <typename T>
 SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_mels, int mel_nnz,
                                         int melp_total = 0) {
   const size_t mel = melp_total > 0
-      ? sizeof(float) * (size_t)round_up4(melp_total) + sizeof(int) * (size_t)round_up4(n_mels)
+      ? sizeof(float) * (size_t)round_up4(2 * melp_total) + sizeof(int) * (size_t)round_up4(n_mels)
       : sizeof(T) * (size_t)round_up4(mel_nnz) + sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
   return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
          sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win + WIN_TAB_PAD)) +
