@@ -2,7 +2,7 @@
 
 There is NO CPU fallback: if the shared library has not been built, or no CUDA device is
 visible, every compute entry point of this package raises.  Build the library with
-``python __graft_entry__.py build`` (or ``make -C single_speaker_tts_b200/csrc``).
+``python __graft_entry__.py build`` (one ``nvcc -shared`` command for sm_100a, see ``build()`` there).
 """
 import ctypes
 import os

@@ -50,6 +50,38 @@ def _make_config(n_fft, win_length, hop_length, precision, sampling_rate=0, n_me
     return cfg
 
 
+SUPPORTED_N_FFT = (512, 1024, 2048)
+
+
+def validate_geometry(n_fft, win_length, hop_length, griffin_lim=False):
+    """The kernels cover the geometries the reference uses (n_fft 2048 / 1102 / 275 for the model,
+    1024 / 1024 / 256 for the statistics and ``time_stretch``) and their neighbourhood, not everything
+    librosa accepts.  Checked here, up front, with a ValueError that names the supported set -- instead
+    of a late ``SsttsError`` from plan creation or a launch that does not fit in shared memory:
+
+      * ``n_fft`` in {512, 1024, 2048};  2 <= ``win_length`` <= ``n_fft`` with ``n_fft - win_length`` even
+        (librosa centres the window with ``(n_fft - win_length) // 2`` zeros on the left);
+      * feature path: 1 <= ``hop_length`` <= ``n_fft``;
+      * Griffin-Lim: 1 <= ``hop_length`` <= ``win_length`` and ``ceil(win_length / hop_length)`` <= 5
+        (at most five frames overlap one sample -- the gather of the overlap-add is unrolled for that).
+    """
+    n_fft, win_length, hop_length = int(n_fft), int(win_length), int(hop_length)
+    if n_fft not in SUPPORTED_N_FFT:
+        raise ValueError('unsupported n_fft={} (supported: 512, 1024, 2048)'.format(n_fft))
+    if not 2 <= win_length <= n_fft:
+        raise ValueError('unsupported win_length={} (need 2 <= win_length <= n_fft={})'.format(win_length, n_fft))
+    if (n_fft - win_length) % 2:
+        raise ValueError('unsupported win_length={}: n_fft - win_length must be even'.format(win_length))
+    if hop_length < 1:
+        raise ValueError('hop_length must be >= 1, got {}'.format(hop_length))
+    if griffin_lim:
+        if hop_length > win_length or -(-win_length // hop_length) > 5:
+            raise ValueError('unsupported hop_length={} for Griffin-Lim with win_length={}: need '
+                             'win_length / 5 <= hop_length <= win_length'.format(hop_length, win_length))
+    elif hop_length > n_fft:
+        raise ValueError('unsupported hop_length={} (need hop_length <= n_fft={})'.format(hop_length, n_fft))
+
+
 class _Plan:
     """Owns one native plan handle; destroyed with the object."""
 
@@ -169,6 +201,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
     compute stream, the host packs sub-batch k + 1 into pinned memory and its H2D copy runs on a
     copy stream.
     """
+    validate_geometry(n_fft, win_length, hop_length, griffin_lim=True)
     lib = _lib.load()
     dev = require_cuda(device)
     n_bins = 1 + n_fft // 2
@@ -280,7 +313,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                     done = torch.cuda.Event()
                     done.record(comp)
                     back.wait_event(done)
-                keep.append((mag_dev, phase_dev, ws, wav_dev, mse_dev))
+                keep.append((mag_dev, phase_dev, ws, wav_dev, mse_dev, plan))   # the plan outlives its launches
             with torch.cuda.stream(back):
                 outs.append((_hostio.download(wav_dev), _hostio.download(mse_dev) if return_mse else None, so, fo))
             if k + 1 < len(ranges):
@@ -292,8 +325,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         if piped:
             back.synchronize()
             copy.synchronize()
-        del keep, nxt, mag_dev, phase_dev, ws, wav_dev, mse_dev
-    _gl_plans.reap()
+        del keep, nxt, mag_dev, phase_dev, ws, wav_dev, mse_dev, plan
+        _gl_plans.reap()
     if flag is not None and int(flag[0]) != 0:
         # same error as the reference's decibel_to_magnitude (audio/conversion.py:47-49)
         raise AssertionError('"conversion.decibel_to_magnitude" was asked to convert a dB value '
@@ -353,16 +386,17 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     _streams / _slot: used by :func:`stft_features_parts` -- (upload, download) side streams; the call
     then returns without synchronising and the caller synchronises both streams.
     """
+    if win_length is None:
+        win_length = n_fft
+    if hop_length is None:
+        hop_length = int(win_length // 4)
+    validate_geometry(n_fft, win_length, hop_length)
     lib = _lib.load()
     dev = require_cuda(device)
     n_bins = 1 + n_fft // 2
     n = len(wavs)
     if n == 0:
         raise ValueError('empty batch')
-    if win_length is None:
-        win_length = n_fft
-    if hop_length is None:
-        hop_length = int(win_length // 4)
     lens = []
     # clips may be handed over as raw 16-bit PCM (all of them): uploaded as 2-byte samples and converted
     # on the device exactly like load_wav does on the host (int16 / 32768)
@@ -453,7 +487,8 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
         if keep_on_device:
             res.spec = torch.view_as_complex(spec_dev) if want_spec else None
             res.lin_db, res.mel_db, res.mel_raw, res.minmax = lin_dev, mel_dev, raw_dev, mm_dev
-            return res
+            res._keep = (wav_dev, pcm_dev, plan)     # the launch may still be running: the plan (its tile
+            return res                               # tables) and the input live as long as the result
 
         back = main
         if _streams is not None:
@@ -463,7 +498,7 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             back.wait_event(done)
             # kept alive until stft_features_parts has synchronised the streams (no record_stream: see
             # griffin_lim_batch)
-            res._keep = (wav_dev, pcm_dev, spec_dev, lin_dev, mel_dev, raw_dev, mm_dev)
+            res._keep = (wav_dev, pcm_dev, spec_dev, lin_dev, mel_dev, raw_dev, mm_dev, plan)
         with torch.cuda.stream(back):
             res.spec = _hostio.download(spec_dev).view(np.complex64).reshape(rows, n_bins) if want_spec else None
             res.lin_db = _hostio.download(lin_dev) if want_lin else None
@@ -472,8 +507,8 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             res.minmax = _hostio.download(mm_dev) if want_minmax else None
         if _streams is None:
             main.synchronize()
-    if _streams is None:
-        _feat_plans.reap()
+            del plan
+            _feat_plans.reap()
     return res
 
 
@@ -502,5 +537,5 @@ def stft_features_parts(wavs, *args, **kwargs):
         streams[0].synchronize()
         for _, _, part in parts:
             part._keep = None
-    _feat_plans.reap()
+        _feat_plans.reap()
     return parts

@@ -5,35 +5,22 @@ hop_length=512; wrapper at audio/effects.py:188-215).
 SURVEY.md section 8f lists this step as the first "next" row (N1) after the STFT hot path.  The
 batched feature path runs it on the device (``sstts_trim_bounds``, used by
 ``features_batch(..., trim=...)`` / ``DatasetHelper.features_from_wavs``); :func:`trim` below is
-the single-clip host utility with the reference's call shape, :func:`trim_batch` the device one.
+the single-clip call with the reference's call shape, :func:`trim_batch` the batched one -- both
+use the same device kernel (no host implementation: the package has no CPU compute path).
 """
 import numpy as np
 
 
-def _frame_mean_square(y, frame_length, hop_length):
-    y = np.pad(np.asarray(y, dtype=np.float32), int(frame_length // 2), mode='reflect')
-    n_frames = 1 + (len(y) - frame_length) // hop_length
-    sq = np.concatenate(([0.0], np.cumsum(y.astype(np.float64) ** 2)))
-    starts = np.arange(n_frames) * hop_length
-    return (sq[starts + frame_length] - sq[starts]) / frame_length
-
-
 def trim(y, top_db=60, frame_length=2048, hop_length=512):
-    """Trim leading and trailing silence: frames whose mean-square energy is more than ``top_db``
-    below the loudest frame.  Returns ``(y[start:end], np.array([start, end]))``."""
+    """Trim leading and trailing silence (``librosa.effects.trim`` with the reference's call shape,
+    audio/effects.py:188-215): frames whose mean-square energy is more than ``top_db`` below the loudest
+    frame.  Returns ``(y[start:end], np.array([start, end]))``.  Runs on the device like everything else
+    in this package (:func:`trim_batch` with one clip); there is no host implementation."""
     y = np.asarray(y)
     if y.size == 0:
         return y, np.asarray([0, 0])
-    mse = _frame_mean_square(y, frame_length, hop_length)
-    ref = max(1e-10, float(mse.max()))
-    db = 10.0 * np.log10(np.maximum(1e-10, mse)) - 10.0 * np.log10(ref)
-    nonzero = np.flatnonzero(db > -top_db)
-    if nonzero.size > 0:
-        start = int(nonzero[0] * hop_length)
-        end = min(y.shape[-1], int((nonzero[-1] + 1) * hop_length))
-    else:
-        start, end = 0, 0
-    return y[start:end], np.asarray([start, end])
+    trimmed, bounds = trim_batch([y], top_db=top_db, frame_length=frame_length, hop_length=hop_length)
+    return trimmed[0], np.asarray([int(bounds[0][0]), int(bounds[0][1])])
 
 
 def trim_batch(wavs, top_db=60, frame_length=2048, hop_length=512):

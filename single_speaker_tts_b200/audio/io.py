@@ -13,9 +13,16 @@ from scipy.io import wavfile
 _IO_THREADS = 8
 
 
-def load_wav(wav_path, offset=0.0, duration=None):
-    """reference audio/io.py:5-30 -- returns ``(float32 mono samples, sampling_rate)``."""
+def load_wav(wav_path, sampling_rate=None, offset=0.0, duration=None):
+    """reference audio/io.py:5-30 (same positional order) -- returns ``(float32 mono samples,
+    sampling_rate)``.  Every caller of the reference loads at the file's own rate
+    (``sampling_rate=None``: datasets/lj_speech.py:114, datasets/statistics.py:90,107,160); a target
+    rate equal to the file's is accepted, another one raises ValueError instead of silently returning
+    un-resampled audio (librosa would resample with resampy, which is not available here)."""
     sr, data = wavfile.read(wav_path)
+    if sampling_rate is not None and int(sampling_rate) != int(sr):
+        raise ValueError('load_wav: resampling is not supported (file rate {} Hz, requested {} Hz); '
+                         'pass sampling_rate=None'.format(sr, sampling_rate))
     if data.dtype == np.int16:
         wav = data.astype(np.float32) / 32768.0
     elif data.dtype == np.int32:

@@ -16,6 +16,14 @@ def _initial_angles(shape):
     return np.exp(2j * np.pi * np.random.rand(*shape))
 
 
+def _check_reanalysis_possible(spectrogram, n_iter):
+    """A single-frame spectrogram gives an EMPTY signal (hop * (T - 1) == 0 samples) whose re-analysis
+    fails in the reference: ``librosa.stft`` reflect-pads it and numpy raises ValueError
+    (audio/synthesis.py:96-106).  The per-item functions keep that error behaviour."""
+    if n_iter > 0 and spectrogram.ndim == 2 and spectrogram.shape[1] == 1:
+        raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
+
+
 def griffin_lim_v2(spectrogram, win_length, hop_length, n_fft, n_iter, angles=None,
                    precision='f32'):
     """Griffin-Lim reconstruction -- reference audio/synthesis.py:43-125.
@@ -25,6 +33,7 @@ def griffin_lim_v2(spectrogram, win_length, hop_length, n_fft, n_iter, angles=No
     ``angles`` (extension) overrides the random initial phase.
     """
     spectrogram = np.asarray(spectrogram)
+    _check_reanalysis_possible(spectrogram, n_iter)
     if angles is None:
         angles = _initial_angles(spectrogram.shape)
     wavs, mses = _runtime.griffin_lim_batch([spectrogram], win_length, hop_length, n_fft, n_iter,
@@ -36,6 +45,7 @@ def griffin_lim_v2(spectrogram, win_length, hop_length, n_fft, n_iter, angles=No
 def spectrogram_to_wav(mag, win_length, hop_length, n_fft, n_iter, angles=None, precision='f32'):
     """Magnitude spectrogram -> float32 waveform -- reference audio/synthesis.py:5-40."""
     mag = np.asarray(mag)
+    _check_reanalysis_possible(mag, n_iter)
     if angles is None:
         angles = _initial_angles(mag.shape)
     wavs, _ = _runtime.griffin_lim_batch([mag], win_length, hop_length, n_fft, n_iter,

@@ -847,6 +847,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
       const int nz = n_rows - n_frames;
       if (A.lin_out) for (int i = tid; i < nz * n_bins; i += NT) A.lin_out[zr0 * n_bins + i] = 0.0f;
       if (A.mel_out) for (int i = tid; i < nz * A.n_mels; i += NT) A.mel_out[zr0 * A.n_mels + i] = 0.0f;
+      if (A.spec_out) for (int i = tid; i < nz * n_bins; i += NT) A.spec_out[zr0 * n_bins + i] = make_float2(0.0f, 0.0f);
+      if (A.melraw_out) for (int i = tid; i < nz * A.n_mels; i += NT) A.melraw_out[zr0 * A.n_mels + i] = 0.0;
     }
 
     float mn_lin = 3.0e38f, mx_lin = -3.0e38f, mn_mel = 3.0e38f, mx_mel = -3.0e38f;

@@ -66,7 +66,13 @@ class DatasetHelper:
         # 16-bit mono files (LJSpeech) go to the device as int16 and are converted there
         for chunk, loaded in prefetch_batches(paths, batch_clips, pcm16=True):
             wavs, srs = zip(*loaded)
-            feats = cls.features_from_wavs(list(wavs), sampling_rate=srs[0])
+            # the mel filterbank depends on the file's own sampling rate (datasets/lj_speech.py:129-131
+            # passes each file's sr): one device batch per distinct rate of the chunk
+            feats = [None] * len(wavs)
+            for sr in sorted(set(srs)):
+                idx = [i for i, r in enumerate(srs) if r == sr]
+                for i, f in zip(idx, cls.features_from_wavs([wavs[i] for i in idx], sampling_rate=sr)):
+                    feats[i] = f
             items = []
             for wav_path, (mel_mag_db, linear_mag_db) in zip(chunk, feats):
                 out_path = '{}.npz'.format(os.path.splitext(wav_path)[0])

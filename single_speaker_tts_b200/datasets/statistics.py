@@ -94,6 +94,11 @@ def collect_reconstruction_error(path_listing, n_iters, batch_clips=64, seed=Non
             by_rate.setdefault(sr, []).append(wav)
         for sr, wavs in by_rate.items():
             mse_errors.extend(reconstruction_errors_from_wavs(wavs, sr, n_iters, seed=seed))
+    # a clip shorter than one hop has a single frame: the reference's griffin_lim_v2 raises for it
+    # (empty re-analysis signal, audio/synthesis.py:96-106); the batched call reports None
+    if any(m is None for m in mse_errors):
+        raise ValueError('collect_reconstruction_error: a clip is shorter than one hop (single-frame '
+                         'spectrogram), Griffin-Lim cannot re-analyse it')
     total_mse = sum(mse_errors) / len(mse_errors)
     print('Dataset MSE with {} iterations: {}'.format(n_iters, total_mse))
     return total_mse

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import librosa_compat as lc            # noqa: E402
 from oracle import reference_audio as ra           # noqa: E402
-from single_speaker_tts_b200.synthetic import make_clips  # noqa: E402
+from single_speaker_tts_b200.synthetic import make_clips, speech_like_clip  # noqa: E402
 
 FIXTURE = ('/root/reference/visualization/data/ljspeech/v1.1/post-processing/'
            'ljspeech-linear-spec-post-215k.npz')
@@ -69,7 +69,52 @@ def features():
     print('features', [out['lin%d' % i].shape for i in range(3)], out['corpus_stats'])
 
 
+def gl_config0():
+    """BASELINE configs[0] exactly: one synthetic 5 s clip (110,250 samples -> T = 401 frames),
+    50 iterations, initial phase from ``RandomState(0)``."""
+    clip = speech_like_clip(5 * 22050, np.random.default_rng(0))
+    mag = np.abs(lc.stft(clip, NFFT, HOP, WIN))
+    assert mag.shape == (1025, 401)
+    angles = np.exp(2j * np.pi * np.random.RandomState(0).rand(*mag.shape))
+    wav, mse = ra.griffin_lim_v2(mag, WIN, HOP, NFFT, 50, angles=angles)
+    np.savez_compressed(os.path.join(HERE, 'gl_config0.npz'), clip=clip, seed=0, n_iter=50,
+                        wav=wav.astype(np.float32), mse=np.float64(mse))
+    print('gl_config0', mag.shape, wav.shape, mse)
+
+
+def gl_fixture_full():
+    """The reference's dumped model output at FULL size -- T = 1000 frames, what
+    tacotron/inference.py:75-101 really feeds (decoder.maximum_iterations, tacotron/params/model.py:108) --
+    through the inference recipe and 50 iterations."""
+    spec = np.load(FIXTURE)['linear_spec'][0, :, :, 0].T        # (1000, 1025)
+    out = np.ascontiguousarray(spec).astype(np.float32)
+    mag = ra.inference_postprocess(out)                           # (1025, 1000)
+    angles = np.exp(2j * np.pi * np.random.RandomState(215).rand(*mag.shape))
+    wav, mse = ra.griffin_lim_v2(mag, WIN, HOP, NFFT, 50, angles=angles)
+    assert wav.shape == (274725,)
+    np.savez_compressed(os.path.join(HERE, 'gl_fixture_full.npz'), model_output=out, seed=215,
+                        n_iter=50, wav=wav.astype(np.float32), mse=np.float64(mse))
+    print('gl_fixture_full', out.shape, wav.shape, mse)
+
+
+def gl_100_iterations():
+    """BASELINE configs[4] runs 100 iterations: two ragged utterances, reported separately because the
+    FP32 drift grows with the iteration count."""
+    clips = [c[:n] for c, n in zip(make_clips(2, seed=44), (2 * 22050, 77000))]
+    out = {}
+    for i, c in enumerate(clips):
+        mag = np.abs(lc.stft(c, NFFT, HOP, WIN))
+        angles = np.exp(2j * np.pi * np.random.RandomState(400 + i).rand(*mag.shape))
+        wav, mse = ra.griffin_lim_v2(mag, WIN, HOP, NFFT, 100, angles=angles)
+        out['clip%d' % i] = c
+        out['wav%d' % i] = wav.astype(np.float32)
+        out['mse%d' % i] = np.float64(mse)
+    np.savez_compressed(os.path.join(HERE, 'gl_100it.npz'), n_iter=100, seed0=400, **out)
+    print('gl_100it', [out['wav%d' % i].shape for i in range(2)])
+
+
 if __name__ == '__main__':
-    gl_fixture()
-    gl_synthetic()
-    features()
+    only = sys.argv[1:]
+    for fn in (gl_fixture, gl_synthetic, features, gl_config0, gl_fixture_full, gl_100_iterations):
+        if not only or fn.__name__ in only:
+            fn()

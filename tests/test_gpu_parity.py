@@ -84,6 +84,104 @@ def test_griffin_lim_50_iterations_real_model_output(golden_dir):
     assert abs(mse - float(g['mse'])) / float(g['mse']) < 1e-2
 
 
+def test_griffin_lim_baseline_config0_401_frames(golden_dir):
+    """BASELINE configs[0] exactly: one 5 s clip, T = 401, 50 iterations, RandomState(0) phase."""
+    g = np.load(golden_dir + '/gl_config0.npz')
+    mag = np.abs(lc.stft(g['clip'], NFFT, HOP, WIN))
+    assert mag.shape == (1025, 401)
+    ang = np.exp(2j * np.pi * np.random.RandomState(int(g['seed'])).rand(*mag.shape))
+    wav, mse = synthesis.griffin_lim_v2(mag, WIN, HOP, NFFT, int(g['n_iter']), angles=ang)
+    err = rel_l2(wav, g['wav'])
+    print('config0 T=401 50 it: rel-L2 %.3e, mse rel err %.3e' % (err, abs(mse - float(g['mse'])) / float(g['mse'])))
+    assert wav.shape == (110000,) and err <= GL_TOL
+    assert abs(mse - float(g['mse'])) / float(g['mse']) < 1e-2
+
+
+def test_griffin_lim_full_1000_frame_model_output(golden_dir):
+    """What tacotron/inference.py:75-101 really feeds: the full (1000, 1025) model output
+    (decoder.maximum_iterations = 1000, tacotron/params/model.py:108), 50 iterations, both through the
+    per-item signature with the oracle's magnitudes and through the fused model-output glue."""
+    g = np.load(golden_dir + '/gl_fixture_full.npz')
+    mag = ra.inference_postprocess(g['model_output'])
+    ang = np.exp(2j * np.pi * np.random.RandomState(int(g['seed'])).rand(*mag.shape))
+    wav, mse = synthesis.griffin_lim_v2(mag, WIN, HOP, NFFT, int(g['n_iter']), angles=ang)
+    err = rel_l2(wav, g['wav'])
+    print('fixture T=1000 50 it: rel-L2 %.3e' % err)
+    assert wav.shape == (274725,) and err <= GL_TOL
+    assert abs(mse - float(g['mse'])) / float(g['mse']) < 1e-2
+    # fused de-normalisation (device float32 exp2) instead of the host recipe: same waveform within budget
+    wavs, _ = _runtime.griffin_lim_batch([g['model_output']], WIN, HOP, NFFT, int(g['n_iter']),
+                                         angles=[ang], denormalize=(6.02, 99.89, 1.3))
+    assert rel_l2(wavs[0], g['wav']) <= GL_TOL
+
+
+def test_griffin_lim_100_iterations_reported_separately(golden_dir):
+    """BASELINE configs[4] runs 100 iterations.  north_star's 1e-3 is stated for 50; FP32 drift grows with
+    the iteration count, so the 100-iteration error is measured and reported on its
+    own, against the looser bound below; the float64 instantiation separates drift from algorithm."""
+    g = np.load(golden_dir + '/gl_100it.npz')
+    clips = [g['clip%d' % i] for i in range(2)]
+    mags = [np.abs(lc.stft(c, NFFT, HOP, WIN)) for c in clips]
+    angs = [np.exp(2j * np.pi * np.random.RandomState(int(g['seed0']) + i).rand(*m.shape)) for i, m in enumerate(mags)]
+    n_iter = int(g['n_iter'])
+    assert n_iter == 100
+    w32 = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, n_iter, angles=angs)
+    w64 = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, n_iter, angles=angs, precision='f64')
+    for i in range(2):
+        e32, e64 = rel_l2(w32[i], g['wav%d' % i]), rel_l2(w64[i], g['wav%d' % i])
+        print('100 it, utterance %d (T=%d): rel-L2 f32 %.3e, f64 %.3e' % (i, mags[i].shape[1], e32, e64))
+        assert e32 <= 5e-3      # reported bound for 100 iterations in FP32 (the stated 1e-3 is for 50)
+        assert e64 <= GL_TOL    # the same kernels in float64 stay inside the 50-iteration budget
+
+
+def test_utterances_sampled_from_the_full_256_batch_match_the_oracle():
+    """BASELINE configs[2] at full size: ONE batched call over the 256 ragged utterances (112,916 frames,
+    sub-batch pipeline, tile tables at full size), 50 iterations, device-seeded phase; four utterances
+    (shortest, longest, two in between) are then checked against the oracle run with the very same
+    initial phasors (read back with sstts_random_phase_at)."""
+    import ctypes
+    clips = make_clips(256, seed=1, pool=16)
+    frames = np.array([1 + len(c) // HOP for c in clips])
+    order = np.argsort(frames)
+    picks = [int(order[0]), int(order[85]), int(order[170]), int(order[-1])]
+    fb = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, want_spec=True, precision='f64')
+    mags = [np.abs(fb.rows(fb.spec, i)).T for i in range(256)]
+    for i in picks:                                   # the oracle's own |STFT| for the checked ones
+        mags[i] = np.abs(lc.stft(clips[i], NFFT, HOP, WIN))
+    seed = 20261018
+    wavs = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=seed)
+    lib = _lib.load()
+    foff = np.concatenate([[0], np.cumsum(frames)])
+    for i in picks:
+        T = int(frames[i])
+        ph = torch.empty((T * 1025, 2), dtype=torch.float32, device='cuda')
+        _lib.check(lib.sstts_random_phase_at(ctypes.c_uint64(seed), int(foff[i]) * 1025, T * 1025,
+                                             ctypes.c_void_p(ph.data_ptr()),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ang = ph.cpu().numpy().view(np.complex64).reshape(T, 1025).T
+        ref = ra.spectrogram_to_wav(mags[i], WIN, HOP, NFFT, 50, angles=ang, batched_fft=True)
+        err = rel_l2(wavs[i], ref)
+        print('utterance %d of the 256-batch (T=%d): rel-L2 %.3e' % (i, T, err))
+        assert wavs[i].shape == ref.shape == (HOP * (T - 1),) and err <= GL_TOL
+
+
+def test_single_frame_spectrogram_follows_the_reference():
+    """T = 1: the reference's per-item functions raise ValueError from the reflect padding of the empty
+    re-analysis signal when n_iter >= 1 (audio/synthesis.py:96-106) and return (empty, None) for
+    n_iter = 0; the batched extension skips such items (empty waveform, mse None) instead of failing
+    the whole batch."""
+    m = np.ones((1025, 1), np.float32)
+    with pytest.raises(ValueError):
+        synthesis.griffin_lim_v2(m, WIN, HOP, NFFT, 2)
+    with pytest.raises(ValueError):
+        synthesis.spectrogram_to_wav(m, WIN, HOP, NFFT, 2)
+    w, mse = synthesis.griffin_lim_v2(m, WIN, HOP, NFFT, 0)
+    assert w.shape == (0,) and w.dtype == np.float32 and mse is None
+    wavs, mses = synthesis.spectrograms_to_wavs([m, np.ones((1025, 3), np.float32)], WIN, HOP, NFFT, 2, seed=1,
+                                                return_mse=True)
+    assert wavs[0].shape == (0,) and mses[0] is None and wavs[1].shape == (2 * HOP,) and mses[1] > 0
+
+
 def test_griffin_lim_dropin_uses_numpy_global_rng():
     x = speech_like_clip(6000, np.random.default_rng(4))
     mag = np.abs(lc.stft(x, NFFT, HOP, WIN))

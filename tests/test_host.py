@@ -12,6 +12,7 @@ import torch
 from oracle import librosa_compat as lc
 from oracle import reference_audio as ra
 from single_speaker_tts_b200 import _lib, _runtime, distributed
+from single_speaker_tts_b200._lib import SsttsError
 from single_speaker_tts_b200.audio import conversion, effects
 from single_speaker_tts_b200.datasets.dataset_helper import DatasetHelper, LJSpeechDatasetHelper
 from single_speaker_tts_b200.datasets.statistics import reduce_decibel_statistics
@@ -73,14 +74,52 @@ def test_conversion_module_equals_oracle():
     assert conversion.samples_to_ms(22050, 22050) == 1000 and conversion.get_duration(np.zeros(44100), 22050) == 2.0
 
 
-def test_trim_equals_oracle():
-    x = np.concatenate([np.zeros(3000, np.float32), speech_like_clip(15000, np.random.default_rng(1)),
-                        1e-5 * np.ones(7000, np.float32)])
-    y, idx = effects.trim(x)
-    yr, idxr = lc.trim(x)
-    assert np.array_equal(idx, idxr) and np.array_equal(y, yr)
-    z, idz = effects.trim(np.zeros(5000, np.float32))
-    assert np.array_equal(idz, lc.trim(np.zeros(5000, np.float32))[1])
+def test_trim_has_no_host_implementation():
+    """audio.effects.trim is the device kernel with the reference's call shape: without a CUDA device it
+    raises like every other compute entry (its values are checked in tests/test_gpu_parity.py and, for the
+    kernel source, in tests/test_emulator.py::test_trim_bounds_match_librosa_trim)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA device present')
+    with pytest.raises(SsttsError):
+        effects.trim(np.ones(5000, np.float32))
+    y, idx = effects.trim(np.zeros(0, np.float32))          # librosa returns the empty clip unchanged
+    assert y.shape == (0,) and tuple(idx) == (0, 0)
+
+
+def test_geometry_is_validated_up_front_with_value_errors():
+    """Unsupported STFT geometries raise ValueError naming the supported set before any device work
+    (they used to surface late as SsttsError from plan creation / 'does not fit')."""
+    v = _runtime.validate_geometry
+    v(2048, 1102, 275, griffin_lim=True); v(1024, 1024, 256, griffin_lim=True); v(512, 512, 128); v(2048, 2048, 2048)
+    for bad in ((4096, 4096, 1024), (2048, 1101, 275), (2048, 2050, 275), (2048, 1102, 0), (2048, 1102, 4096)):
+        with pytest.raises(ValueError, match='unsupported|must be'):
+            v(*bad)
+    for bad in ((2048, 1102, 137), (2048, 1102, 1200)):          # win / hop > 5, hop > win
+        with pytest.raises(ValueError, match='Griffin-Lim'):
+            v(*bad, griffin_lim=True)
+    with pytest.raises(ValueError, match='unsupported n_fft'):    # raised before the CUDA check
+        _runtime.griffin_lim_batch([np.ones((2049, 4), np.float32)], 4096, 1024, 4096, 1)
+    with pytest.raises(ValueError, match='unsupported n_fft'):
+        _runtime.stft_features_batch([np.ones(5000, np.float32)], 4096, 1024, 4096)
+
+
+def test_load_wav_keeps_the_reference_signature(tmp_path):
+    """audio/io.py:5 -- load_wav(wav_path, sampling_rate=None, offset=0.0, duration=None): the second
+    positional argument is the target rate, not an offset."""
+    from scipy.io import wavfile
+    from single_speaker_tts_b200.audio.io import load_wav
+    x = (np.arange(22050) % 100 - 50).astype(np.int16) * 200
+    path = str(tmp_path / 'a.wav')
+    wavfile.write(path, 22050, x)
+    w, sr = load_wav(path)
+    assert sr == 22050 and w.dtype == np.float32 and len(w) == 22050
+    w2, _ = load_wav(path, 22050)                      # same rate: accepted, full clip (not offset = 22050 s)
+    assert np.array_equal(w, w2)
+    w3, _ = load_wav(path, None, 0.5, 0.25)
+    assert np.array_equal(w3, w[11025:11025 + 5512])
+    with pytest.raises(ValueError, match='resampling'):
+        load_wav(path, 16000)
 
 
 def test_reduction_padding_equals_oracle():

@@ -151,6 +151,37 @@ def test_fixture_recipe(golden_dir):
     assert g['wav'].shape == (HOP * 159,)                    # 275 * (T - 1)
 
 
+def test_real_shape_goldens_regression(golden_dir):
+    """The goldens at the shapes the reference really runs (BASELINE configs[0]: T = 401; the full
+    1000-frame model output of tacotron/params/model.py:108; 100 iterations as in configs[4]) are
+    what this oracle produces today, and obey the known answers: T = 1 + N // hop, length hop * (T - 1)."""
+    g = np.load(golden_dir + '/gl_config0.npz')
+    mag = np.abs(lc.stft(g['clip'], NFFT, HOP, WIN))
+    assert mag.shape == (1025, 401) and g['wav'].shape == (110000,)
+    ang = np.exp(2j * np.pi * np.random.RandomState(int(g['seed'])).rand(*mag.shape))
+    wav, mse = ra.griffin_lim_v2(mag, WIN, HOP, NFFT, int(g['n_iter']), angles=ang, batched_fft=True)
+    assert np.linalg.norm(wav - g['wav']) / np.linalg.norm(g['wav']) < 1e-5
+    assert abs(mse - float(g['mse'])) / float(g['mse']) < 1e-5
+    f = np.load(golden_dir + '/gl_fixture_full.npz')
+    assert f['model_output'].shape == (1000, 1025) and f['wav'].shape == (274725,)     # SURVEY 8c known answer
+    mag = ra.inference_postprocess(f['model_output'])
+    assert mag.shape == (1025, 1000) and mag.dtype == np.float32 and mag.min() > 0
+    h = np.load(golden_dir + '/gl_100it.npz')
+    assert int(h['n_iter']) == 100
+    for i in range(2):
+        assert h['wav%d' % i].shape == (HOP * (len(h['clip%d' % i]) // HOP),)
+
+
+def test_single_frame_spectrogram_raises_like_the_reference():
+    """audio/synthesis.py:96-106 with T = 1: istft returns an empty signal and the stft's reflect
+    padding of an empty array raises ValueError in numpy; n_iter = 0 returns (empty, None)."""
+    m = np.ones((1025, 1), np.float32)
+    with pytest.raises(ValueError):
+        ra.griffin_lim_v2(m, WIN, HOP, NFFT, 1)
+    w, mse = ra.griffin_lim_v2(m, WIN, HOP, NFFT, 0)
+    assert w.shape == (0,) and mse is None
+
+
 def test_pavoque_recipe_restatement_shapes_and_floor():
     """datasets/pavoque.py:104-160: zeroed bins sit on the normalised -100 dB floor (0.0 with
     ref 24 / max 100) and the row slice comes from silence_interval_from_spectrogram as written."""
