@@ -107,6 +107,14 @@ int sstts_griffin_lim_seeded(const sstts_gl_plan* plan, const float* mag_dev, ui
  * is below float32 tiny.  wav_dev is the wav_out_dev of sstts_griffin_lim for the same plan. */
 int sstts_peak_normalize(const sstts_gl_plan* plan, float* wav_dev, void* stream);
 
+/* Unit phasors from host-drawn uniforms -- the device half of audio/synthesis.py:85
+ * `np.exp(2j * np.pi * np.random.rand(bins, T))`: the per-item functions keep the reference's use of
+ * numpy's global random stream, so the host draws the uniforms and uploads them as they are.
+ * uniform_dev: (n_bins, n_frames) float64, bin-major like np.random.rand(bins, T); phase_dev:
+ * (n_frames, n_bins) interleaved (re, im) float32 = exp(2 pi i u) in the layout sstts_griffin_lim reads. */
+int sstts_phase_from_uniform(const double* uniform_dev, int64_t n_frames, int n_bins, float* phase_dev,
+                             void* stream);
+
 /* Fill n unit phasors exp(2 pi i u), u ~ U[0, 1) from a counter-based generator keyed by seed
  * (batched extension: replaces the host-side np.random.rand of audio/synthesis.py:85). */
 int sstts_random_phase(uint64_t seed, int64_t n, float* phase_dev, void* stream);

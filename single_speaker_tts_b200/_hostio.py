@@ -104,8 +104,14 @@ def _pack_and_copy(views, srcs, sizes, stage, out, itemsize_row):
     array (a task hand-over costs as much as copying ~100 KB)."""
     starts = np.concatenate([[0], np.cumsum(sizes)])
     per_chunk = max(1, _CHUNK_BYTES // itemsize_row)
-    ex = _pool()
     n = len(srcs)
+    if n <= 2 and int(starts[-1]) * itemsize_row <= (16 << 20):
+        # the single-utterance path (tacotron/serve.py:39-86): a hand-over to the worker threads costs more
+        # than copying a few megabytes in place
+        _copy_group(list(zip(views, srcs)))
+        out[:starts[-1]].copy_(stage[:starts[-1]], non_blocking=True)
+        return
+    ex = _pool()
     i = 0
     while i < n:
         j = i

@@ -57,6 +57,8 @@ SIGNATURES = {
                                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p]),
     'sstts_peak_normalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'sstts_phase_from_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_void_p]),
     'sstts_random_phase': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p,
                                           ctypes.c_void_p]),
     'sstts_random_phase_at': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,

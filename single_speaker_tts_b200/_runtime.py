@@ -181,7 +181,8 @@ def _split_by_frames(frames, first, growth=1):
 
 
 def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, seed=None,
-                      precision='f32', return_mse=False, device=None, denormalize=None, normalize_peak=False):
+                      precision='f32', return_mse=False, device=None, denormalize=None, normalize_peak=False,
+                      uniform=None):
     """Griffin-Lim for a ragged batch (reference: audio/synthesis.py:43-125, one call per item).
 
     mags   : list of (1 + n_fft/2, T_i) magnitude spectrograms (any float dtype / layout).
@@ -189,6 +190,11 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
              ``np.exp(2j*pi*np.random.rand(...))``); if None they are generated on the device from
              ``seed`` (seed=None draws one 63-bit seed from numpy's global RNG, so
              ``np.random.seed`` still makes a run reproducible).
+    uniform : optional list of float64 ``(1 + n_fft/2, T_i)`` arrays of U[0, 1) numbers, the reference's
+             ``np.random.rand(*spectrogram.shape)`` (audio/synthesis.py:85): uploaded as drawn and turned
+             into the initial phasors ``exp(2j * pi * u)`` on the device (the per-item functions use this
+             to keep numpy's global random stream without paying for the complex exponential and the
+             transposing copy on the host).
     denormalize : None, or ``(ref_db, max_db, power)``: ``mags`` then holds the model's normalised
              outputs in its own orientation ``(T_i, 1 + n_fft/2)`` and the glue of
              tacotron/inference.py:94-101,175 (inv_normalize_decibel -> decibel_to_magnitude ->
@@ -219,10 +225,11 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         frames.append(m.shape[1])
     if return_mse and n_iter < 1:
         raise ValueError('mse needs n_iter >= 1')
-    if angles is not None:
-        if len(angles) != n:
+    if angles is not None or uniform is not None:
+        given = angles if angles is not None else uniform
+        if len(given) != n:
             raise ValueError('need one initial phase array per spectrogram')
-        for a, m in zip(angles, mags):
+        for a, m in zip(given, mags):
             if a.shape != m.shape:
                 raise ValueError('initial phase shape {} != spectrogram shape {}'.format(a.shape, m.shape))
     elif seed is None:
@@ -245,12 +252,18 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
 
         return _gl_plans.get(key, factory), fo
 
-    with torch.cuda.device(dev):
+    # All work runs on streams private to the calling thread (inputs and outputs are host arrays, so
+    # nothing has to be ordered against the caller's current stream): concurrent callers -- the six
+    # synthesis threads of tacotron/serve.py:69-72 -- then overlap on the device instead of queueing
+    # behind each other on the default stream.
+    with torch.cuda.device(dev), torch.cuda.stream(_aux_stream(dev, 'gl0')):
         main = torch.cuda.current_stream()
         piped = len(ranges) > 1
         copy = _aux_stream(dev, 'h2d') if piped else main     # uploads
         back = _aux_stream(dev, 'd2h') if piped else main     # result downloads (other DMA direction)
         compute = [main, _aux_stream(dev, 'gl1')] if piped else [main]
+
+        keep = []
 
         def upload(k):
             """Pack + H2D of sub-batch k on the copy stream; returns device tensors and an event."""
@@ -263,6 +276,18 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                     ph_dev = torch.view_as_real(_hostio.upload_rows(
                         [np.asarray(a).T for a in angles[i0:i1]], n_bins, torch.complex64, dev,
                         slot='phase%d' % (k & 1)))
+                elif uniform is not None:
+                    u_dev = _hostio.upload_flat([np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+                                                 for u in uniform[i0:i1]], torch.float64, dev,
+                                                slot='uni%d' % (k & 1))
+                    ph_dev = torch.empty((int(sum(frames[i0:i1])), n_bins, 2), dtype=torch.float32, device=dev)
+                    o = 0
+                    for t in frames[i0:i1]:
+                        _lib.check(lib.sstts_phase_from_uniform(
+                            ctypes.c_void_p(u_dev.data_ptr() + 8 * o * n_bins), t, n_bins,
+                            ctypes.c_void_p(ph_dev.data_ptr() + 8 * o * n_bins), _stream_ptr()))
+                        o += t
+                    keep.append(u_dev)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             return mag_dev, ph_dev, ev
@@ -277,7 +302,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         # and fall back to cudaMalloc in the next call -- every tensor is kept alive in `keep` until all
         # streams have been synchronised at the end of the call: then freeing is hazard-free and the next
         # call finds exactly the blocks it needs in the allocator's per-stream caches.
-        keep = [flag_dev]
+        keep.append(flag_dev)
         outs = []
         nxt = upload(0)
         for k, (i0, i1) in enumerate(ranges):
@@ -359,6 +384,7 @@ class FeatureBatch:
         self.minmax = None    # (n_clips, 4) float64
         self.mel_basis = None
         self.trim_bounds = None  # (n_clips, 2) int64 (start, end) when trimming was requested
+        self.done = None         # pipelined call: CUDA event after the last download of this batch
         self._keep = None        # device tensors of a pipelined call, released after its final sync
 
     def rows(self, arr, i, padded=False):
@@ -366,6 +392,48 @@ class FeatureBatch:
         if not padded:
             b = a + self.frames[i]
         return arr[a:b]
+
+
+class DeviceClips:
+    """Decoded clips resident on the device: one packed float32 buffer and the per-clip lengths.
+    Produced by :func:`upload_clips`; :func:`stft_features_batch` accepts it in place of the host list,
+    so a corpus pass uploads every clip once and runs the statistics and the pre-calculation kernels on
+    the same buffer (datasets/statistics.py:89 and datasets/lj_speech.py:114 each decode the file again
+    in the reference)."""
+
+    def __init__(self, wav_dev, lens, keep=None, ready=None):
+        self.wav_dev = wav_dev
+        self.lens = [int(v) for v in lens]
+        self.keep = keep          # e.g. the int16 upload the float buffer was converted from
+        self.ready = ready        # CUDA event: the upload / conversion has finished
+
+    def __len__(self):
+        return len(self.lens)
+
+
+def upload_clips(wavs, device=None, stream=None, slot=0):
+    """Pack + upload a list of 1-D clips (float32, or all int16 PCM) once; returns :class:`DeviceClips`.
+    ``stream``: side stream to run the copy (and the PCM conversion) on; the returned object carries the
+    event consumers have to wait for."""
+    lib = _lib.load()
+    dev = require_cuda(device)
+    wavs = list(wavs)
+    pcm16 = all(getattr(w, 'dtype', None) == np.int16 for w in wavs)
+    if not pcm16 and any(getattr(w, 'dtype', None) == np.int16 for w in wavs):
+        wavs = [(w.astype(np.float32) / 32768.0) if w.dtype == np.int16 else w for w in wavs]
+    lens = [int(w.shape[0]) for w in wavs]
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            up = _hostio.upload_flat(wavs, torch.int16 if pcm16 else torch.float32, dev, slot='clips%d' % (slot & 1))
+            keep = None
+            if pcm16:
+                keep = up
+                up = torch.empty(keep.shape, dtype=torch.float32, device=dev)
+                _lib.check(lib.sstts_pcm16_to_float(_ptr(keep), int(sum(lens)), _ptr(up), _stream_ptr()))
+            ev = torch.cuda.Event()
+            ev.record(st)
+    return DeviceClips(up, lens, keep=keep, ready=ev)
 
 
 def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None, n_mels=0, fmin=0.0,
@@ -398,17 +466,23 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     if n == 0:
         raise ValueError('empty batch')
     lens = []
+    resident = wavs if isinstance(wavs, DeviceClips) else None
     # clips may be handed over as raw 16-bit PCM (all of them): uploaded as 2-byte samples and converted
     # on the device exactly like load_wav does on the host (int16 / 32768)
-    pcm16 = all(getattr(w, 'dtype', None) == np.int16 for w in wavs)
-    if not pcm16 and any(getattr(w, 'dtype', None) == np.int16 for w in wavs):
-        wavs = [(w.astype(np.float32) / 32768.0) if w.dtype == np.int16 else w for w in wavs]   # mixed list
-    for w in wavs:
-        if w.ndim != 1:
-            raise ValueError('Invalid shape for monophonic audio: ndim={:d}'.format(w.ndim))
-        if w.shape[0] < 1:
+    pcm16 = resident is None and all(getattr(w, 'dtype', None) == np.int16 for w in wavs)
+    if resident is not None:
+        lens = list(resident.lens)
+        if min(lens) < 1:
             raise ValueError('clip is empty')
-        lens.append(w.shape[0])
+    else:
+        if not pcm16 and any(getattr(w, 'dtype', None) == np.int16 for w in wavs):
+            wavs = [(w.astype(np.float32) / 32768.0) if w.dtype == np.int16 else w for w in wavs]   # mixed list
+        for w in wavs:
+            if w.ndim != 1:
+                raise ValueError('Invalid shape for monophonic audio: ndim={:d}'.format(w.ndim))
+            if w.shape[0] < 1:
+                raise ValueError('clip is empty')
+            lens.append(w.shape[0])
     sample_off = _offsets(lens)
     need_mel = want_mel or want_mel_raw or want_minmax
     cfg = _make_config(n_fft, win_length, hop_length, precision, sampling_rate if need_mel else 0,
@@ -419,7 +493,11 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     trim_bounds = None
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
-        if _streams is not None:
+        if resident is not None:
+            wav_dev = resident.wav_dev
+            if resident.ready is not None:
+                main.wait_event(resident.ready)
+        elif _streams is not None:
             with torch.cuda.stream(_streams[0]):
                 wav_dev = _hostio.upload_flat(wavs, torch.int16 if pcm16 else torch.float32, dev,
                                               slot='wav%d' % (_slot & 1))
@@ -505,6 +583,9 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
             res.mel_db = _hostio.download(mel_dev) if want_mel else None
             res.mel_raw = _hostio.download(raw_dev) if want_mel_raw else None
             res.minmax = _hostio.download(mm_dev) if want_minmax else None
+            if _streams is not None:
+                res.done = torch.cuda.Event()
+                res.done.record(back)
         if _streams is None:
             main.synchronize()
             del plan

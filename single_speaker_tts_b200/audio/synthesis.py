@@ -11,9 +11,10 @@ import numpy as np
 from .. import _runtime
 
 
-def _initial_angles(shape):
-    # reference audio/synthesis.py:85
-    return np.exp(2j * np.pi * np.random.rand(*shape))
+def _initial_uniform(shape):
+    # reference audio/synthesis.py:85 draws np.random.rand(*spectrogram.shape) from numpy's GLOBAL stream;
+    # the exp(2j * pi * u) around it runs on the device (sstts_phase_from_uniform)
+    return np.random.rand(*shape)
 
 
 def _check_reanalysis_possible(spectrogram, n_iter):
@@ -24,32 +25,44 @@ def _check_reanalysis_possible(spectrogram, n_iter):
         raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
 
 
+def _phase_arguments(shape, angles, device_phase):
+    if angles is not None:
+        return {'angles': [angles]}
+    if device_phase:
+        # one 63-bit seed from numpy's global stream (np.random.seed still makes the call reproducible);
+        # the phasors themselves come from the counter-based generator inside the first launch
+        return {'seed': int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))}
+    return {'uniform': [_initial_uniform(shape)]}
+
+
 def griffin_lim_v2(spectrogram, win_length, hop_length, n_fft, n_iter, angles=None,
-                   precision='f32'):
+                   precision='f32', device_phase=False):
     """Griffin-Lim reconstruction -- reference audio/synthesis.py:43-125.
 
     Returns ``(audio float32 of length hop*(T-1), mse)``; ``mse`` is the mean squared magnitude
     error of the last iteration (None when ``n_iter`` == 0, like the reference).
-    ``angles`` (extension) overrides the random initial phase.
+    ``angles`` (extension) overrides the random initial phase; ``device_phase=True`` (extension)
+    draws it on the device instead of taking ``np.random.rand(*shape)`` from numpy's global stream --
+    the 1,025 x T host draws cost several times the whole reconstruction of one utterance and are
+    serialised across threads by the RandomState lock (tacotron/serve.py:69-72 calls from six threads).
     """
     spectrogram = np.asarray(spectrogram)
     _check_reanalysis_possible(spectrogram, n_iter)
-    if angles is None:
-        angles = _initial_angles(spectrogram.shape)
+    phase = _phase_arguments(spectrogram.shape, angles, device_phase)
     wavs, mses = _runtime.griffin_lim_batch([spectrogram], win_length, hop_length, n_fft, n_iter,
-                                            angles=[angles], precision=precision,
-                                            return_mse=n_iter > 0)
+                                            precision=precision, return_mse=n_iter > 0, **phase)
     return wavs[0], (mses[0] if mses is not None else None)
 
 
-def spectrogram_to_wav(mag, win_length, hop_length, n_fft, n_iter, angles=None, precision='f32'):
-    """Magnitude spectrogram -> float32 waveform -- reference audio/synthesis.py:5-40."""
+def spectrogram_to_wav(mag, win_length, hop_length, n_fft, n_iter, angles=None, precision='f32',
+                       device_phase=False):
+    """Magnitude spectrogram -> float32 waveform -- reference audio/synthesis.py:5-40 (``angles`` /
+    ``device_phase``: see :func:`griffin_lim_v2`)."""
     mag = np.asarray(mag)
     _check_reanalysis_possible(mag, n_iter)
-    if angles is None:
-        angles = _initial_angles(mag.shape)
+    phase = _phase_arguments(mag.shape, angles, device_phase)
     wavs, _ = _runtime.griffin_lim_batch([mag], win_length, hop_length, n_fft, n_iter,
-                                         angles=[angles], precision=precision)
+                                         precision=precision, **phase)
     return wavs[0].astype(np.float32)
 
 

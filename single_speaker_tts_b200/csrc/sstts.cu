@@ -221,15 +221,39 @@ int max_optin_smem() {
   return v;
 }
 
+// Per (kernel, device, threads, shared-memory size): the opt-in shared-memory attribute is set once and the
+// occupancy is queried once -- both are driver calls of several microseconds, far too slow to repeat on every
+// call of the single-utterance path (tacotron/serve.py:69-72 calls spectrogram_to_wav per sentence).
+struct KernelConfigKey {
+  const void* fn; int device, threads; size_t smem;
+  bool operator<(const KernelConfigKey& o) const {
+    return std::tie(fn, device, threads, smem) < std::tie(o.fn, o.device, o.threads, o.smem);
+  }
+};
+std::mutex g_kcfg_mu;
+std::map<KernelConfigKey, int> g_kcfg;          // -> resident blocks per SM
+std::map<std::pair<const void*, int>, bool> g_kattr;   // (kernel, device) -> attribute set
+
 template <typename K>
 int configure_kernel(K kernel, int threads, size_t smem, int* blocks_per_sm) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  const KernelConfigKey key{reinterpret_cast<const void*>(kernel), dev, threads, smem};
+  std::lock_guard<std::mutex> lock(g_kcfg_mu);
+  auto it = g_kcfg.find(key);
+  if (it != g_kcfg.end()) { *blocks_per_sm = it->second; return 0; }
   const int limit = max_optin_smem();
   if (limit <= 0 || smem > (size_t)limit)
     return fail(SSTTS_ERR_CUDA, "kernel does not fit on this device (shared memory)");
-  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
+  bool& attr_set = g_kattr[std::make_pair(key.fn, dev)];
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
+    attr_set = true;
+  }
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
   if (occ < 1) return fail(SSTTS_ERR_CUDA, "kernel does not fit on this device (shared memory / registers)");
+  g_kcfg[key] = occ;
   *blocks_per_sm = occ;
   return 0;
 }
@@ -404,6 +428,23 @@ __global__ void random_phase_kernel(unsigned long long seed, long long first, lo
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = seeded_phasor(seed, first + i);
+}
+
+// audio/synthesis.py:85: angles = exp(2j * pi * np.random.rand(bins, T)).  The per-item functions keep the
+// reference's use of numpy's GLOBAL random stream; the host only draws the uniforms (bin-major, like
+// np.random.rand(bins, T)) and this kernel turns them into frame-major unit phasors -- the complex
+// exponential and the transpose to the device layout are the expensive part on the host.
+__global__ void phase_from_uniform_kernel(const double* __restrict__ u, long long n_frames, int n_bins,
+                                          float2* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_frames * n_bins; i += stride) {
+    const long long t = i / n_bins;
+    const int k = (int)(i - t * n_bins);
+    double s, c;
+    sincospi(2.0 * u[(long long)k * n_frames + t], &s, &c);
+    out[i] = make_float2((float)c, (float)s);
+  }
 }
 
 // tacotron/inference.py:94-101,175: normalised model output -> dB (inv_normalize_decibel) ->
@@ -624,6 +665,18 @@ int sstts_random_phase_at(uint64_t seed, int64_t first, int64_t n, float* phase_
   if (blocks > 148 * 16) blocks = 148 * 16;
   random_phase_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       seed, first, n, reinterpret_cast<float2*>(phase_dev));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int sstts_phase_from_uniform(const double* uniform_dev, int64_t n_frames, int n_bins, float* phase_dev, void* stream) {
+  if (n_frames < 0 || n_bins < 1 || (n_frames > 0 && (!uniform_dev || !phase_dev)))
+    return fail(SSTTS_ERR_INVALID, "bad phase_from_uniform arguments");
+  if (n_frames == 0) return 0;
+  long long blocks = (n_frames * n_bins + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  phase_from_uniform_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      uniform_dev, n_frames, n_bins, reinterpret_cast<float2*>(phase_dev));
   CU(cudaGetLastError());
   return 0;
 }

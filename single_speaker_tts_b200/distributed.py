@@ -79,3 +79,74 @@ def corpus_decibel_statistics(local_wavs, local_indices, n_total, sampling_rate,
         rows.append(np.asarray(per_clip_fn(local_wavs[s:s + batch_clips], sampling_rate)))
     local_rows = np.concatenate(rows, axis=0) if rows else np.zeros((0, 4))
     return reduce_corpus_statistics(local_rows, local_indices, n_total, group=group)
+
+
+def corpus_pass(local_wavs, local_indices, n_total, sampling_rate, n_fft, hop_length, win_length, n_mels, fmin,
+                fmax, reduction=5, group=None, chunk_samples=6 << 20, sink=None, precision='f64'):
+    """BASELINE configs[3] on this rank's shard: ``tacotron/dataset_statistics.py`` followed by
+    ``tacotron/dataset_precalc_features.py`` with the constants the first one printed.
+
+      1. every clip is packed and uploaded ONCE (chunks of ``chunk_samples`` samples; the upload of chunk
+         k + 1 overlaps the statistics kernel of chunk k) and stays on the device;
+      2. per-clip ``[min lin, max lin, min mel, max mel]`` dB (datasets/statistics.py:11-66) -> the one
+         exchange step of the path: :func:`reduce_corpus_statistics` (all-reduce) -> the float64 mean in
+         listing order that the reference prints as ``linear_mag_max_db, linear_ref_db, mel_mag_max_db,
+         mel_mag_ref_db`` (tacotron/dataset_statistics.py:35-39);
+      3. the feature kernel (datasets/lj_speech.py:124-156) runs on the resident clips with those
+         constants; results travel back on a download stream into page-locked blocks while the next
+         chunk is transformed, and are handed to ``sink(global_indices, FeatureBatch)`` (numpy views of
+         the blocks, no second host copy) two chunks behind the device.
+
+    Returns ``(mean4, n_rows)``; ``n_rows`` counts the feature rows (frames padded to the reduction factor)
+    this rank produced."""
+    from . import _runtime
+    dev = _runtime.require_cuda()
+    local_wavs = list(local_wavs)
+    ranges = _runtime._split_by_frames([int(w.shape[0]) for w in local_wavs], chunk_samples) if local_wavs else []
+    resident, stats = [], []
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        copy, back = _runtime._aux_stream(dev, 'h2d'), _runtime._aux_stream(dev, 'd2h')
+        nxt = _runtime.upload_clips(local_wavs[ranges[0][0]:ranges[0][1]], dev, copy, 0) if ranges else None
+        for k in range(len(ranges)):
+            clips = nxt
+            if k + 1 < len(ranges):
+                nxt = _runtime.upload_clips(local_wavs[ranges[k + 1][0]:ranges[k + 1][1]], dev, copy, k + 1)
+            res = _runtime.stft_features_batch(clips, 1024, 256, 1024, sampling_rate=sampling_rate, n_mels=80,
+                                               fmin=0, fmax=sampling_rate // 2, want_minmax=True,
+                                               precision=precision, keep_on_device=True)
+            resident.append(clips)
+            stats.append(res)
+        main.synchronize()
+        local_rows = (torch.cat([r.minmax for r in stats]).cpu().numpy() if stats else np.zeros((0, 4)))
+        del stats
+    mean4, _, _, _ = reduce_corpus_statistics(local_rows, local_indices, n_total, group=group)
+    lin_max, lin_ref, mel_max, mel_ref = mean4          # tacotron/dataset_statistics.py:35-39
+    n_rows = 0
+    with torch.cuda.device(dev):
+        pending = []
+
+        def retire(limit):
+            nonlocal n_rows
+            while len(pending) > limit:
+                (i0, i1), part = pending.pop(0)
+                part.done.synchronize()
+                n_rows += int(part.row_off[-1])
+                if sink is not None:
+                    sink(local_indices[i0:i1], part)
+                part._keep = None
+
+        for k, clips in enumerate(resident):
+            part = _runtime.stft_features_batch(clips, n_fft, hop_length, win_length, sampling_rate=sampling_rate,
+                                                n_mels=n_mels, fmin=fmin, fmax=fmax, reduction=reduction,
+                                                want_lin=True, want_mel=True,
+                                                normalize=(lin_ref, lin_max, mel_ref, mel_max),
+                                                precision=precision, _streams=(copy, back), _slot=k)
+            pending.append((ranges[k], part))
+            retire(2)
+        retire(0)
+        main.synchronize()
+        back.synchronize()
+        del resident
+        _runtime._feat_plans.reap()
+    return mean4, n_rows

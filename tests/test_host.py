@@ -180,11 +180,14 @@ def test_bench_reference_arm_line_shape():
     import sys
     env = dict(os.environ, RANK='0', WORLD_SIZE='1')
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
-                          '--warmup', '0'], capture_output=True, text=True, env=env, timeout=600)
+                          '--warmup', '0', '--ref-items', '4'], capture_output=True, text=True, env=env, timeout=600)
     line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
     d = json.loads(line)
     assert d['impl'] == 'reference' and d['unit'] == 'audio-s/s' and d['value'] > 0
     assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+    import bench
+    assert d['config'] == bench.workload_config()          # both arms state the same workload
+    assert d['metric'] == 'griffin_lim_50it_audio_sec_per_sec' and d['higher_is_better'] is True
 
 
 def test_gl_sub_batch_split_covers_every_utterance_once():
