@@ -56,4 +56,44 @@ __device__ __forceinline__ float sstts_sqrt_approx(float x) {
 __device__ __forceinline__ void sstts_cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
+// ---- bulk asynchronous copies (the 1-D form of TMA) completing on a shared-memory mbarrier ----
+// One thread arms the barrier with the byte count and issues the copies; the copy engine moves the data
+// (no per-lane address arithmetic, no registers), everybody waits on the barrier's phase parity.
+typedef unsigned long long sstts_mbar_t;
+__device__ __forceinline__ void sstts_mbar_init(sstts_mbar_t* bar, unsigned arrivals) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(arrivals));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+// the issuing thread's arrival + the number of bytes the copies of this phase will deliver
+__device__ __forceinline__ void sstts_mbar_arrive_expect_tx(sstts_mbar_t* bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy; all three of dst, src, bytes are multiples of 16
+__device__ __forceinline__ void sstts_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, sstts_mbar_t* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(a) : "memory");
+}
+__device__ __forceinline__ void sstts_mbar_phase_done(sstts_mbar_t*) {}   // emulator hook (see cpu_simt.h)
+__device__ __forceinline__ void sstts_mbar_wait(sstts_mbar_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later asynchronous-proxy
+// (bulk copy) accesses: issued before a buffer that was read / written with ordinary instructions is
+// handed back to the copy engine
+__device__ __forceinline__ void sstts_fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
 #endif

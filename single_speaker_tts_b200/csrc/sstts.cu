@@ -634,6 +634,8 @@ static int griffin_lim_dispatch(const sstts_gl_plan* P, const float* mag_dev, co
   if (!P || !mag_dev || !workspace_dev || n_iter < 0) return fail(SSTTS_ERR_INVALID, "bad griffin_lim arguments");
   if (P->host.total_samples > 0 && !wav_out_dev) return fail(SSTTS_ERR_INVALID, "wav_out_dev is NULL");
   if (mse_frame_dev && n_iter < 1) return fail(SSTTS_ERR_INVALID, "mse needs n_iter >= 1");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 15)
+    return fail(SSTTS_ERR_INVALID, "workspace_dev must be 16-byte aligned (bulk copies read it in 16-byte units)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
 #define GL_CALL(T, G, W) run_griffin_lim<T, G, W>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \

@@ -344,19 +344,33 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)[32], c
 }
 
 // Shared-memory carve-up of the Griffin-Lim step kernel.
+// SSTTS_GL_BULK (default 1): interior tiles of the float32 iteration kernel take their input span with bulk
+// asynchronous copies (cp.async.bulk + mbarrier, the 1-D form of TMA) issued by ONE thread while the CTA is
+// still transforming the previous tile, instead of every thread loading, normalising and storing its
+// samples after the gather.  0 keeps the synchronous staging everywhere (A/B builds, tools/ab_bench.sh).
+#ifndef SSTTS_GL_BULK
+#define SSTTS_GL_BULK 1
+#endif
+template <typename T> SSTTS_HD constexpr bool gl_uses_bulk() { return SSTTS_GL_BULK != 0 && sizeof(T) == 4; }
+
 template <typename T> struct GLSmem {
   typedef typename cx_of<T>::type C;
   int plane_elems;   // per-warp plane: transpose tile, later the windowed output frame
-  size_t off_w2k, off_win, off_rw, off_plane, off_mag, off_yin, total;
+  int edge_elems;    // one neighbour edge region ((win - hop) samples + alignment slack)
+  size_t off_w2k, off_win, off_wr, off_rw, off_plane, off_mag, off_yin, off_edge, off_bar, total;
   SSTTS_HD GLSmem(int warps, int win, int hop, int span_max) {
     plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
+    edge_elems = round_up4(win - hop > 0 ? win - hop : 0) + 8;
     size_t o = sizeof(C) * 1024;
     off_w2k = o; o += sizeof(C) * 512;
     off_win = o; o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
+    off_wr = o; if (gl_uses_bulk<T>()) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_rw = o; o += sizeof(T) * round_up4(hop);
     off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
     off_mag = o; o += sizeof(float) * (size_t)warps * MAGROW;
-    off_yin = o; o += sizeof(T) * round_up4(span_max);
+    off_yin = o; o += sizeof(T) * (round_up4(span_max) + 8);      // + slack for the 16-byte alignment shift
+    off_edge = o; if (gl_uses_bulk<T>()) o += sizeof(T) * 2 * (size_t)edge_elems;
+    off_bar = o; o += 16;                                          // mbarrier + arrival counter
     total = o;
   }
 };
@@ -388,12 +402,27 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   float* s_mag = reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
   T* s_yin = reinterpret_cast<T*>(smem + L.off_yin);
   T* plane = s_planes + warp * L.plane_elems;
+  constexpr bool BULK = !FROM_PHASE && gl_uses_bulk<T>();
+  T* s_wrtab = reinterpret_cast<T*>(smem + L.off_wr);           // window x reciprocal window sum (BULK)
+  T* s_wr = s_wrtab + win_shift(lpad);
+  T* s_edge = reinterpret_cast<T*>(smem + L.off_edge);          // raw neighbour sums of the two edge regions
+  sstts_mbar_t* s_bar = reinterpret_cast<sstts_mbar_t*>(smem + L.off_bar);
+  int* s_cnt = reinterpret_cast<int*>(smem + L.off_bar + 8);    // warps that have consumed s_yin this round
 
   for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
+  if (BULK && tid == 0) { sstts_mbar_init(s_bar, 1); *s_cnt = 0; }
   __syncthreads();
   fill_interior_rwss<T>(s_rw, s_win, hop, win, tid, NT, inv_nfft);
   __syncthreads();
+  if (BULK) {
+    // interior samples: x = (own + neighbour) * rw[(m - lpad) mod hop], then * window[m - lpad] in the window
+    // load; the residue only depends on the position inside the frame, so both factors fold into one table
+    for (int i = tid; i < round_up4(win + WIN_TAB_PAD); i += NT) {
+      const int j = i - win_shift(lpad);
+      s_wrtab[i] = (j >= 0 && j < win) ? s_win[j] * s_rw[j % hop] : T(0);
+    }
+  }
 
   // Tile records are single independent 48-byte loads, issued two rounds ahead.
   struct TileCtx { int a, b, parity, n_frames; long long f0, poff; };
@@ -403,6 +432,52 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     c.a = tl.a; c.b = tl.b; c.parity = tl.parity;
     c.f0 = tl.f0; c.n_frames = tl.n_frames; c.poff = tl.poff;
     return c;
+  };
+
+  // common case ("plain" tile): no reflection inside the span and every sample covered by a full set of frames
+  auto is_plain = [&](const TileCtx& tl) -> bool {
+    const int L_out = hop * (tl.n_frames - 1);
+    const int span_lo = tl.a * hop + lpad;
+    const int span = (tl.b - tl.a - 1) * hop + win;
+    return (span_lo >= cpad) && (span_lo + span - cpad <= L_out) && (tl.a * hop >= win - hop) &&
+           ((tl.a * hop + span - 1) / hop <= tl.n_frames - 1);
+  };
+  // BULK: one thread hands the span of a plain tile to the copy engine -- the tile's own-parity sums into
+  // s_yin and the neighbour-parity sums of the two edge regions into s_edge -- and arms the barrier with
+  // the byte count.  Sources are rounded down to 16 bytes: sample s of the span lands at s_yin[s + mis],
+  // left-edge sample s at s_edge[s + mis], right-edge sample s (>= rb) at s_edge[edge_elems + s - rb + mis_r].
+  auto bulk_issue = [&](const TileCtx& tl) {
+    const int span_lo = tl.a * hop + lpad;
+    const int span = (tl.b - tl.a - 1) * hop + win;
+    const T* own = (tl.parity ? A.pin1 : A.pin0) + tl.poff + span_lo;
+    const T* oth = (tl.parity ? A.pin0 : A.pin1) + tl.poff + span_lo;
+    const int mis = span_lo & 3;                       // poff and the buffers are 16-byte aligned
+    const int le = win - hop, rb = (tl.b - tl.a) * hop;
+    const int mis_r = (span_lo + rb) & 3;
+    const unsigned b_own = (unsigned)sizeof(T) * (unsigned)round_up4(span + mis);
+    const unsigned b_le = (unsigned)sizeof(T) * (unsigned)round_up4(le + mis);
+    const unsigned b_re = (unsigned)sizeof(T) * (unsigned)round_up4(span - rb + mis_r);
+    sstts_fence_proxy_async();
+    sstts_mbar_arrive_expect_tx(s_bar, b_own + b_le + b_re);
+    sstts_bulk_g2s(s_yin, own - mis, b_own, s_bar);
+    sstts_bulk_g2s(s_edge, oth - mis, b_le, s_bar);
+    sstts_bulk_g2s(s_edge + L.edge_elems, oth + rb - mis_r, b_re, s_bar);
+    sstts_mbar_phase_done(s_bar);
+  };
+  // ... and everybody completes it: wait for the bytes, add the neighbour's contribution inside the two edge
+  // regions (the normalisation is folded into the window table, see s_wr above)
+  unsigned bar_parity = 0;
+  auto bulk_finish = [&](const TileCtx& tl) {
+    const int span_lo = tl.a * hop + lpad;
+    const int span = (tl.b - tl.a - 1) * hop + win;
+    const int mis = span_lo & 3;
+    const int le = win - hop, rb = (tl.b - tl.a) * hop;
+    const int mis_r = (span_lo + rb) & 3;
+    sstts_mbar_wait(s_bar, bar_parity);
+    bar_parity ^= 1u;
+    for (int s = tid; s < le; s += NT) s_yin[s + mis] += s_edge[s + mis];
+    const T* er = s_edge + L.edge_elems + mis_r - rb;
+    for (int s = rb + tid; s < span; s += NT) s_yin[s + mis] += er[s];
   };
 
   // Stage the analysis input of a tile: x_pad[span] = y_norm[reflect], y_norm = OLA sum / wss.
@@ -419,9 +494,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     // next tile's (disjoint because tiles hold >= min_tile frames)
     const int le = a > 0 ? win - hop : 0;
     const int rb = b < n_frames ? (b - a) * hop : 0x7fffffff;
-    // common case: no reflection inside the span and every sample covered by a full set of frames
-    const bool plain = (span_lo >= cpad) && (span_lo + span - cpad <= L_out) && (a * hop >= win - hop) &&
-                       ((a * hop + span - 1) / hop <= n_frames - 1);
+    const bool plain = is_plain(tl);
     if (plain) {
       const T* own = pin_own + span_lo;
       const T* oth = pin_oth + span_lo;
@@ -468,7 +541,17 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   TileCtx cur = {0, 0, 0, 0, 0, 0}, nxt = {0, 0, 0, 0, 0, 0}, nxt2 = {0, 0, 0, 0, 0, 0};
   if (tile < A.n_tiles) cur = load_ctx(tile);
   if (tile + (int)gridDim.x < A.n_tiles) nxt = load_ctx(tile + gridDim.x);
-  if (!FROM_PHASE && tile < A.n_tiles) stage(cur);
+  bool cur_bulk = false;          // the current tile's s_yin holds raw sums at an alignment offset (BULK path)
+  if (!FROM_PHASE && tile < A.n_tiles) {
+    cur_bulk = BULK && is_plain(cur);
+    if (cur_bulk) {
+      __syncthreads();            // s_wr and the barrier initialisation are visible
+      if (tid == 0) bulk_issue(cur);
+      bulk_finish(cur);
+    } else {
+      stage(cur);
+    }
+  }
   __syncthreads();
 
   while (tile < A.n_tiles) {
@@ -497,21 +580,23 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       } else {
         const int mis = stage_row_async(s_mag, mrow, lane, n_bins);
         srow = s_mag + mis;
-        const T* fin = s_yin + warp * hop - lpad;  // fin[m], m in [lpad, lpad + win)
+        // bulk-staged tiles hold raw sums shifted by the alignment offset; their normalisation is in s_wr
+        const T* fin = s_yin + (cur_bulk ? ((a * hop + lpad) & 3) : 0) + warp * hop - lpad;  // fin[m], m in [lpad, lpad + win)
+        const T* wtab = cur_bulk ? s_wr : s_win;
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
           const int m = 64 * n1 + 2 * lane;
           const int i = m - lpad;
           // window pair (zero outside the window) in one aligned load; DIT pass: bit-reversed slots
           C w2; w2.x = T(0); w2.y = T(0);
-          if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
+          if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(wtab + i);
           re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
           im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
         }
 #ifndef SSTTS_STAGE_PREFETCH
 #define SSTTS_STAGE_PREFETCH 1
 #endif
-        if (SSTTS_STAGE_PREFETCH && next < A.n_tiles) {
+        if (SSTTS_STAGE_PREFETCH && !BULK && next < A.n_tiles) {
           // the next tile's span of both parity buffers is pulled into L2 while this tile is transformed
           // (one 128-byte line per thread, no registers held), so the synchronous staging after the
           // gather waits for an L2 hit instead of DRAM.  Placed after the window load: the tile record
@@ -527,6 +612,15 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
           }
         }
         warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
+        if (BULK) {
+          // this warp's samples have been consumed by the transform: the last of the tile's warps to get
+          // here hands s_yin back to the copy engine for the NEXT tile, whose span then arrives while the
+          // CTA is busy with the core, the inverse transform and the gather of this one
+          if (lane == 0 && atomicAdd(s_cnt, 1) == FT - 1) {
+            *s_cnt = 0;
+            if (next < A.n_tiles && is_plain(nxt)) bulk_issue(nxt);
+          }
+        }
         sstts_cp_async_wait_all();
         __syncwarp();
       }
@@ -607,7 +701,10 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         }
       }
     }
-    if (!FROM_PHASE && next < A.n_tiles) stage(nxt);
+    if (!FROM_PHASE && next < A.n_tiles) {
+      cur_bulk = BULK && is_plain(nxt);
+      if (cur_bulk) bulk_finish(nxt); else stage(nxt);
+    }
     __syncthreads();
     tile = next;
     cur = nxt;

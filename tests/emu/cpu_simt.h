@@ -159,6 +159,21 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 
+// bulk copies + mbarrier: the copy is a synchronous memcpy by the issuing thread, a completed phase bumps an
+// atomic counter (sstts_mbar_phase_done, a no-op on the device where the copy engine completes the
+// phase), waiters spin until the phase of the given parity is over.
+typedef unsigned long long sstts_mbar_t;
+static inline void sstts_mbar_init(sstts_mbar_t* bar, unsigned) { __atomic_store_n(bar, 0ULL, __ATOMIC_RELEASE); }
+static inline void sstts_mbar_arrive_expect_tx(sstts_mbar_t*, unsigned) {}
+static inline void sstts_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, sstts_mbar_t*) {
+  std::memcpy(smem_dst, gmem_src, bytes);
+}
+static inline void sstts_mbar_phase_done(sstts_mbar_t* bar) { __atomic_fetch_add(bar, 1ULL, __ATOMIC_RELEASE); }
+static inline void sstts_mbar_wait(sstts_mbar_t* bar, unsigned parity) {
+  while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ULL) == (unsigned long long)parity) std::this_thread::yield();
+}
+static inline void sstts_fence_proxy_async() {}
+
 template <typename V> static inline V atomicAdd(V* p, V v) {
   std::lock_guard<std::mutex> g(emu::atomic_mutex());
   V old = *p; *p = old + v; return old;

@@ -2,7 +2,7 @@
 # A/B several builds of libsstts on the GPU box: tools/ab_bench.sh lib1.so lib2.so ...
 for lib in "$@"; do
   echo "== $lib"
-  SSTTS_LIB=$PWD/$lib python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+  SSTTS_LIB=$PWD/$lib python bench.py --workload gl256 --steps 5 --warmup 3 2>&1 | python -c "
 import sys, json
 for line in sys.stdin:
     if line.startswith('{'):
