@@ -211,6 +211,66 @@ SSTTS_HD void fft32(T (&re)[32], T (&im)[32]) {
   }
 }
 
+SSTTS_HD constexpr int brev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
+
+// In-register 16-point DIT FFT over the slots BASE .. BASE + 15: element n in slot BASE + brev4(n) ->
+// result k in slot BASE + k.  W_16^j = W_32^(2 j), so the butterflies are the ones of the 32-point pass.
+template <typename T, bool INV, int BASE>
+SSTTS_HD void fft16_dit(T (&re)[32], T (&im)[32]) {
+#pragma unroll
+  for (int g = 0; g < 16; g += 2) dit_butterfly<T, INV>(re[BASE + g], im[BASE + g], re[BASE + g + 1], im[BASE + g + 1], 0);
+#pragma unroll
+  for (int g = 0; g < 16; g += 4) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) dit_butterfly<T, INV>(re[BASE + g + j], im[BASE + g + j], re[BASE + g + j + 2], im[BASE + g + j + 2], j * 8);
+  }
+#pragma unroll
+  for (int g = 0; g < 16; g += 8) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dit_butterfly<T, INV>(re[BASE + g + j], im[BASE + g + j], re[BASE + g + j + 4], im[BASE + g + j + 4], j * 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dit_butterfly<T, INV>(re[BASE + j], im[BASE + j], re[BASE + j + 8], im[BASE + j + 8], j * 2);
+}
+
+// 512-point complex FFT (= real FFT of n_fft = 1024) on HALF a warp: the 16 lanes of a half own one
+// transform, so a warp carries two frames at once.  Element index = 16 * slot + hl (hl = lane & 15) on the
+// way in (bit-reversed slots, like the DIT first pass of warp_fft1024); 512 = 32 x 16:
+//     pass 1  32-point FFT over the slot index (registers)
+//     twiddle W_512^(hl * k1)          tw[k1 * 16 + hl]
+//     32 x 16 transpose through the half's shared-memory plane (pitch 17; the second half's plane starts
+//             16 banks further, so the 32 lanes of a warp-wide access never collide)
+//     pass 2  two 16-point FFTs: slots 0..15 for k1 = hl, slots 16..31 for k1 = hl + 16
+// Result: slot s holds Z[k], k = hl + (s & 16) + 32 * (s & 15).
+constexpr int HPITCH = 17;
+constexpr int HPLANE_ELEMS = 32 * HPITCH + 16;      // 560: + 16 puts the second half on the other 16 banks
+template <typename T>
+SSTTS_D void halfwarp_fft512(T (&re)[32], T (&im)[32], T* xh, const typename cx_of<T>::type* tw, int hl) {
+  typedef typename cx_of<T>::type C;
+  fft32<T, false, true>(re, im);
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) {
+    const C w = tw[k1 * 16 + hl];
+    const T vr = re[k1], vi = im[k1];
+    re[k1] = vr * w.x - vi * w.y;
+    im[k1] = vr * w.y + vi * w.x;
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) xh[k1 * HPITCH + hl] = re[k1];
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < 32; ++s) re[(s & 16) + brev4(s & 15)] = xh[(hl + (s & 16)) * HPITCH + (s & 15)];
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) xh[k1 * HPITCH + hl] = im[k1];
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < 32; ++s) im[(s & 16) + brev4(s & 15)] = xh[(hl + (s & 16)) * HPITCH + (s & 15)];
+  __syncwarp();
+  fft16_dit<T, false, 0>(re, im);
+  fft16_dit<T, false, 16>(re, im);
+}
+
 // Per-warp transpose tile: one scalar plane of 32 x 33 (pitch 33 keeps the column-wise stores
 // and the row-wise loads bank-conflict free).  Real and imaginary parts go through the same
 // plane one after the other, which halves the shared memory per warp compared with a complex

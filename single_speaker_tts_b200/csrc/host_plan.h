@@ -112,8 +112,22 @@ struct FeatPlanHost {
 
 // clip_start[c] / clip_len[c]: first sample and length of clip c inside the packed wav buffer
 // (clips need not be contiguous: trimmed clips keep their place in the untrimmed upload).
+// The feature kernel transforms n_fft = 1024 natively (two frames per warp, 16-frame tiles); 2048 and 512 go
+// through the 2048-point transform (512 embedded in it).
+inline bool feat_native_1024(int n_fft) { return n_fft == 1024; }
+
+// Frames per tile: one frame per warp and round (kTileFrames), or -- native n_fft 1024 path -- two frames per
+// warp of the CTA (float32: 8 warps, float64: kFeatWarpsF64 warps; a larger tile would push the float64
+// kernel's sample buffers past the shared memory that lets two CTAs share an SM).
+inline int feat_tile_frames(int n_fft, bool f64) {
+  if (!feat_native_1024(n_fft)) return kTileFrames;
+  const int t = 2 * (f64 ? kFeatWarpsF64 : kWarps);
+  return t < kNativeTileFrames ? t : kNativeTileFrames;
+}
+
 inline bool build_feat_plan(int n_clips, const long long* clip_start, const long long* clip_len, int n_fft,
-                            int win, int hop, int reduction, FeatPlanHost& P, std::string& err) {
+                            int win, int hop, int reduction, FeatPlanHost& P, std::string& err, bool f64 = false) {
+  const int tile_frames = feat_tile_frames(n_fft, f64);
   if (n_fft != 2048 && n_fft != 1024 && n_fft != 512) { err = "n_fft must be 2048, 1024 or 512"; return false; }
   if (win < 2 || win > n_fft || hop < 1) { err = "need hop >= 1 and 2 <= win <= n_fft"; return false; }
   if ((n_fft - win) % 2 != 0) { err = "n_fft - win_length must be even"; return false; }
@@ -132,8 +146,8 @@ inline bool build_feat_plan(int n_clips, const long long* clip_start, const long
     const long long rows = ((T + reduction - 1) / reduction) * reduction;
     P.frame_off[c + 1] = P.frame_off[c] + T;
     P.row_off[c + 1] = P.row_off[c] + rows;
-    for (long long a = 0; a < T; a += kTileFrames) {
-      FeatTile t; t.clip = c; t.a = (int)a; t.b = (int)((a + kTileFrames < T) ? a + kTileFrames : T);
+    for (long long a = 0; a < T; a += tile_frames) {
+      FeatTile t; t.clip = c; t.a = (int)a; t.b = (int)((a + tile_frames < T) ? a + tile_frames : T);
       t.last = (t.b == T) ? 1 : 0;
       P.tiles.push_back(t);
       const int span = (t.b - t.a - 1) * hop + win;
@@ -163,6 +177,28 @@ inline void make_tables(int win, std::vector<double>& tw1024, std::vector<double
   }
   window.resize(win);
   // scipy.signal.get_window('hann', win, fftbins=True): 0.5 - 0.5 cos(2 pi n / win)
+  for (int n = 0; n < win; ++n) window[n] = 0.5 - 0.5 * std::cos(2.0 * pi * n / win);
+}
+
+// Tables of the native n_fft = 1024 feature path (halfwarp_fft512), in the slots the kernel loads:
+// tw[k1 * 16 + hl] = exp(-2 pi i k1 hl / 512) (k1 < 32, hl < 16; padded to the 1024 entries the prologue
+// copies), w[k] = exp(-2 pi i k / 1024) (k < 512), and the periodic Hann window.
+inline void make_tables_native1024(int win, std::vector<double>& tw512, std::vector<double>& w1024,
+                                   std::vector<double>& window) {
+  const double pi = 3.14159265358979323846264338327950288;
+  tw512.assign(2 * 1024, 0.0);
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int hl = 0; hl < 16; ++hl) {
+      const int e = (k1 * hl) % 512;
+      tw512[2 * (k1 * 16 + hl)] = std::cos(2.0 * pi * e / 512.0);
+      tw512[2 * (k1 * 16 + hl) + 1] = -std::sin(2.0 * pi * e / 512.0);
+    }
+  w1024.resize(2 * 1024);
+  for (int k = 0; k < 1024; ++k) {
+    w1024[2 * k] = std::cos(2.0 * pi * k / 1024.0);
+    w1024[2 * k + 1] = -std::sin(2.0 * pi * k / 1024.0);
+  }
+  window.resize(win);
   for (int n = 0; n < win; ++n) window[n] = 0.5 - 0.5 * std::cos(2.0 * pi * n / win);
 }
 

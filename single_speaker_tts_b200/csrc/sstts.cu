@@ -59,9 +59,10 @@ struct DeviceTables {
 };
 
 template <typename T>
-int upload_tables(int win, DeviceTables& D) {
+int upload_tables(int win, bool native1024, DeviceTables& D) {
   std::vector<double> tw, w2, wn;
-  make_tables(win, tw, w2, wn);
+  if (native1024) make_tables_native1024(win, tw, w2, wn);
+  else make_tables(win, tw, w2, wn);
   std::vector<T> a(tw.begin(), tw.end()), b(w2.begin(), w2.end()), c(wn.begin(), wn.end());
   T *da, *db, *dc;
   int rc;
@@ -97,24 +98,28 @@ struct StaticTables {
   void* d_mel_w = nullptr;
   float* d_melp_w = nullptr;
 };
-typedef std::tuple<int, int, int, int, int, int, double, double> StaticKey;
+typedef std::tuple<int, int, int, int, int, int, double, double, int> StaticKey;
 std::mutex g_static_mu;
 std::map<StaticKey, std::shared_ptr<StaticTables> > g_static;
 
-int get_static_tables(const sstts_stft_config* cfg, int device, bool with_mel, std::shared_ptr<StaticTables>* out) {
+// native1024: tables of the feature kernel's native n_fft = 1024 transform (the Griffin-Lim kernels embed
+// n_fft = 1024 in the 2048-point transform and use the ordinary tables).
+int get_static_tables(const sstts_stft_config* cfg, int device, bool with_mel, bool native1024,
+                      std::shared_ptr<StaticTables>* out) {
   const bool f64 = cfg->precision == SSTTS_F64;
   const int n_mels = with_mel ? cfg->n_mels : 0;
   const double fmax = n_mels > 0 ? (cfg->mel_fmax > 0 ? cfg->mel_fmax : cfg->sampling_rate / 2.0) : 0.0;
   const StaticKey key(device, cfg->precision, cfg->n_fft, cfg->win_length, n_mels > 0 ? cfg->sampling_rate : 0, n_mels,
-                      n_mels > 0 ? cfg->mel_fmin : 0.0, fmax);
+                      n_mels > 0 ? cfg->mel_fmin : 0.0, fmax, native1024 ? 1 : 0);
   std::lock_guard<std::mutex> lock(g_static_mu);
   auto it = g_static.find(key);
   if (it != g_static.end()) { *out = it->second; return 0; }
   std::shared_ptr<StaticTables> S(new StaticTables());
-  int rc = f64 ? upload_tables<double>(cfg->win_length, S->tab) : upload_tables<float>(cfg->win_length, S->tab);
+  int rc = f64 ? upload_tables<double>(cfg->win_length, native1024, S->tab)
+               : upload_tables<float>(cfg->win_length, native1024, S->tab);
   if (!rc && n_mels > 0) {
     make_mel_csr(cfg->sampling_rate, cfg->n_fft, n_mels, cfg->mel_fmin, fmax, S->mel, &S->mel_dense);
-    make_mel_padded(S->mel, n_mels, FEAT_PLANE_ELEMS, S->melp);
+    make_mel_padded(S->mel, n_mels, native1024 ? HMAG : FEAT_PLANE_ELEMS, S->melp);
     rc = upload(S->mel.ptr, &S->d_mel_ptr);
     if (!rc) rc = upload(S->mel.k0, &S->d_mel_k0);
     if (!rc && S->melp.ok) rc = upload(S->melp.w, &S->d_melp_w);
@@ -202,7 +207,7 @@ int check_config(const sstts_stft_config* cfg, bool allow_embedded) {
 bool is_model_geometry(int n_fft, int win, int hop) { return n_fft == 2048 && win == 1102 && hop == 275; }
 bool is_stats_geometry(int n_fft, int win, int hop) { return n_fft == 1024 && win == 1024 && hop == 256; }
 typedef StaticGeom<1102, 275, 2048> ModelGeom;   // tacotron/params/model.py:13-24
-typedef StaticGeom<1024, 256, 1024> StatsGeom;   // datasets/statistics.py:31-34
+typedef NativeGeom1024<1024, 256> StatsGeom;     // datasets/statistics.py:31-34 (native 512-point complex transform)
 
 int sm_count() {
   int dev = 0, n = 0;
@@ -323,7 +328,7 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
   cudaError_t e = cudaGetDevice(&P->device);
   if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
   P->n_sms = sm_count();
-  rc = get_static_tables(cfg, P->device, false, &P->st);
+  rc = get_static_tables(cfg, P->device, false, false, &P->st);
   if (!rc) {
     const size_t o0 = P->blob.add(P->host.frame_off), o1 = P->blob.add(P->host.pad_off);
     const size_t o2 = P->blob.add(P->host.sample_off), o3 = P->blob.add(P->host.tiles);
@@ -592,9 +597,11 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   A.n_fft = P->cfg.n_fft;
   if (A.n_mels < 1) { A.mel_out = nullptr; A.melraw_out = nullptr; }
 
-  // the pre-calculation configuration runs the fused dB-feature mode of the kernel
-  const bool fast = S.melp.ok && S.d_melp_w && A.n_fft == NFFT && A.lin_out && A.mel_out && !A.spec_out &&
-                    !A.melraw_out && !A.minmax_out && A.mel_power == 1.0f && !O->force_generic;
+  // the pre-calculation configuration (n_fft 2048: linear + mel dB) and the statistics configuration (native
+  // n_fft 1024: any of per-clip extrema / linear dB / mel dB) run the fused float32-epilogue mode of the kernel
+  const bool fused_ok = S.melp.ok && S.d_melp_w && !A.spec_out && !A.melraw_out && A.mel_power == 1.0f && !O->force_generic;
+  const bool fast = fused_ok && (feat_native_1024(A.n_fft) ? (A.lin_out || A.mel_out || A.minmax_out)
+                                                           : (A.n_fft == NFFT && A.lin_out && A.mel_out && !A.minmax_out));
   A.melp_w = S.d_melp_w;
   A.melp_slots = fast ? S.melp.n_slots : 0;
   A.melp_total = fast ? S.melp.total : 0;
@@ -768,7 +775,7 @@ int sstts_feat_plan_create_ranges(const sstts_stft_config* cfg, int n_clips, con
   std::string err;
   std::vector<long long> cs(clip_start_host, clip_start_host + n_clips), cl(clip_len_host, clip_len_host + n_clips);
   if (!build_feat_plan(n_clips, cs.data(), cl.data(), cfg->n_fft, cfg->win_length, cfg->hop_length, reduction,
-                       P->host, err)) {
+                       P->host, err, cfg->precision == SSTTS_F64)) {
     delete P;
     return fail(SSTTS_ERR_INVALID, err);
   }
@@ -776,7 +783,7 @@ int sstts_feat_plan_create_ranges(const sstts_stft_config* cfg, int n_clips, con
   if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
   P->n_sms = sm_count();
   if (cfg->n_mels > 0 && cfg->sampling_rate < 1) { sstts_feat_plan_destroy(P); return fail(SSTTS_ERR_INVALID, "sampling_rate must be > 0"); }
-  rc = get_static_tables(cfg, P->device, cfg->n_mels > 0, &P->st);
+  rc = get_static_tables(cfg, P->device, cfg->n_mels > 0, feat_native_1024(cfg->n_fft), &P->st);
   if (!rc) {
     const size_t o0 = P->blob.add(P->host.sample_off), o1 = P->blob.add(P->host.sample_len);
     const size_t o2 = P->blob.add(P->host.frame_off), o3 = P->blob.add(P->host.row_off);
@@ -842,13 +849,16 @@ int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const ss
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
   const bool stats = is_stats_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
+  const bool native = feat_native_1024(P->cfg.n_fft);
   if (P->cfg.precision == SSTTS_F64) {
     if (model) return run_features<double, ModelGeom, kFeatWarpsF64>(P, wav_dev, out, st);
     if (stats) return run_features<double, StatsGeom, kFeatWarpsF64>(P, wav_dev, out, st);
+    if (native) return run_features<double, DynGeom1024, kFeatWarpsF64>(P, wav_dev, out, st);
     return run_features<double, DynGeom, kFeatWarpsF64>(P, wav_dev, out, st);
   }
   if (model) return run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st);
   if (stats) return run_features<float, StatsGeom, kWarps>(P, wav_dev, out, st);
+  if (native) return run_features<float, DynGeom1024, kWarps>(P, wav_dev, out, st);
   return run_features<float, DynGeom, kWarps>(P, wav_dev, out, st);
 }
 

@@ -43,6 +43,7 @@ constexpr int NBINS = HALF + 1;    // 1025
 // NFFT_EFF samples of the zero-padded buffer and only every (2048 / NFFT_EFF)-th bin is kept
 // (zero padding in time interpolates the spectrum, so those bins ARE the NFFT_EFF-point DFT).
 template <int WIN, int HOP, int NFFT_EFF = 2048> struct StaticGeom {
+  static constexpr bool kNative1024 = false;
   SSTTS_HD StaticGeom(int, int, int) {}
   SSTTS_HD constexpr int win() const { return WIN; }
   SSTTS_HD constexpr int hop() const { return HOP; }
@@ -54,7 +55,36 @@ template <int WIN, int HOP, int NFFT_EFF = 2048> struct StaticGeom {
   static constexpr int ZLO = ((NFFT_EFF - WIN) / 2) / 64;
   static constexpr int ZHI = ((NFFT_EFF - WIN) / 2 + WIN - 1) / 64;
 };
+// n_fft = 1024 transformed natively by the feature kernel: a 512-point complex FFT on half a warp, two
+// frames per warp (halfwarp_fft512) -- the geometry of datasets/statistics.py:31-34 and of the STFT in
+// audio/effects.py:71-77 -- instead of the 2048-point transform with every other bin dropped.
+template <int WIN, int HOP> struct NativeGeom1024 {
+  SSTTS_HD NativeGeom1024(int, int, int) {}
+  SSTTS_HD constexpr int win() const { return WIN; }
+  SSTTS_HD constexpr int hop() const { return HOP; }
+  SSTTS_HD constexpr int nfft() const { return 1024; }
+  SSTTS_HD constexpr int lpad() const { return (1024 - WIN) / 2; }
+  SSTTS_HD constexpr int cpad() const { return 512; }
+  SSTTS_HD constexpr int bin_shift() const { return 1; }
+  static constexpr int ZLO = 0;
+  static constexpr int ZHI = 31;
+  static constexpr bool kNative1024 = true;
+};
+struct DynGeom1024 {
+  int win_, hop_;
+  SSTTS_HD DynGeom1024(int w, int h, int) : win_(w), hop_(h) {}
+  SSTTS_HD int win() const { return win_; }
+  SSTTS_HD int hop() const { return hop_; }
+  SSTTS_HD constexpr int nfft() const { return 1024; }
+  SSTTS_HD int lpad() const { return (1024 - win_) / 2; }
+  SSTTS_HD constexpr int cpad() const { return 512; }
+  SSTTS_HD constexpr int bin_shift() const { return 1; }
+  static constexpr int ZLO = 0;
+  static constexpr int ZHI = 31;
+  static constexpr bool kNative1024 = true;
+};
 struct DynGeom {
+  static constexpr bool kNative1024 = false;
   int win_, hop_, nfft_;
   SSTTS_HD DynGeom(int w, int h, int n) : win_(w), hop_(h), nfft_(n) {}
   SSTTS_HD int win() const { return win_; }
@@ -819,7 +849,9 @@ SSTTS_D long long encode_ordered(double v) {
 #define kDbPerLog2Mag 6.020599913279624f
 #define kDbPerLog2Pow 3.010299956639812f
 
-constexpr int FEAT_PLANE_ELEMS = 1056;  // >= XPLANE_ELEMS and >= NBINS floats
+constexpr int FEAT_PLANE_ELEMS = 1120;  // >= XPLANE_ELEMS, >= NBINS floats and >= 2 * HPLANE_ELEMS
+constexpr int kNativeTileFrames = 16;   // frames per tile of the native n_fft 1024 path (two per warp and round)
+constexpr int HMAG = 544;               // per-half |S| row of the native path: 513 bins + zero slack for padded filters
 
 // MODE = FeatMode::kGeneric: every output is optional and selected at run time.
 // MODE = FeatMode::kDbFeatures: the pre-calculation configuration (datasets/lj_speech.py:106-156) --
@@ -949,6 +981,147 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
     }
 
     float mn_lin = 3.0e38f, mx_lin = -3.0e38f, mn_mel = 3.0e38f, mx_mel = -3.0e38f;
+    if constexpr (G::kNative1024) {
+      // n_fft = 1024 natively: two frames per warp, the 16 lanes of a half own one 512-point complex transform
+      // (halfwarp_fft512).  Z[k] sits in slot s of lane hl with k = hl + (s & 16) + 32 (s & 15); the conjugate
+      // partner Z[512 - k] of a lower-set bin (s < 16) is in the upper set of lane (16 - hl) & 15, slot 31 - s;
+      // lane hl == 0 holds both members of its pairs: slots (j, 16 - j) and (16 + j, 31 - j), plus the DC /
+      // Nyquist pair in slot 0 and the self-conjugate bin 256 in slot 8.
+      // FAST (fused mode): float32 epilogue like the n_fft 2048 dB-feature mode -- any of linear dB, mel dB and
+      // the per-clip extrema (the statistics pass, datasets/statistics.py:54-66: the extrema of the dB values
+      // are the dB values of the extrema, so only min / max of |X|^2 and of the mel sums are tracked per bin).
+      const int half = lane >> 4, hl = lane & 15;
+      T* xh = plane + half * HPLANE_ELEMS;
+      float* s_mag2 = reinterpret_cast<float*>(plane);          // after the transposes: |S| rows of both frames
+      const int partner = (lane & 16) | ((16 - hl) & 15);
+      float pmin = 3.0e38f, pmax = 0.0f, mmin = 3.0e38f, mmax = 0.0f;   // FAST: extrema of 4 |X|^2 and of 2 mel
+      for (int jp = warp; 2 * jp < FT; jp += W) {
+        const bool live = 2 * jp + half < FT;
+        const int jr = live ? 2 * jp + half : 2 * jp;           // an odd tile's last half redoes its sibling, stores nothing
+        const long long row = r0 + a + jr;
+        T re[32], im[32];
+        const float* fin = s_xc + mis_cur + jr * hop - lpad;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int m = 32 * n1 + 2 * hl;
+          const int i = m - lpad;
+          C w2; w2.x = T(0); w2.y = T(0);
+          if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
+          re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * w2.x : T(0);
+          im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * w2.y : T(0);
+        }
+        halfwarp_fft512<T>(re, im, xh, s_tw, hl);
+        float* s_mag = s_mag2 + half * HMAG;
+        float* lin_row = (FAST && A.lin_out) ? A.lin_out + row * n_bins : nullptr;
+        // one bin, given 2 X[ko]; librosa stores X as complex64, everything downstream is float32
+        auto emit = [&](int ko, T xr2, T xi2) {
+          if (FAST) {
+            const float fr = (float)xr2, fi = (float)xi2;       // an exact power-of-two multiple of the complex64 value
+            const float p4 = fmaf(fr, fr, fi * fi);             // 4 |X|^2
+            s_mag[ko] = sstts_sqrt_approx(p4);                  // 2 |X| for the mel projection
+            pmin = fminf(pmin, p4);
+            pmax = fmaxf(pmax, p4);
+            if (lin_row) lin_row[ko] = fminf(fmaxf(fmaf(sstts_log2_ftz(fmaxf(4e-10f, p4)), fl_a, fl_b), clip_lo), clip_hi);
+          } else {
+            const float fr = (float)(T(0.5) * xr2), fi = (float)(T(0.5) * xi2);
+            if (A.spec_out) A.spec_out[row * n_bins + ko] = make_float2(fr, fi);
+            const float p = fmaf(fr, fr, fi * fi);
+            if (want_mel) s_mag[ko] = sstts_sqrt_approx(p);
+            if (want_lin_db) {
+              const float d = kDbPerLog2Pow * sstts_log2_approx(fmaxf(1e-10f, p));
+              mn_lin = fminf(mn_lin, d);
+              mx_lin = fmaxf(mx_lin, d);
+              if (want_lin) A.lin_out[row * n_bins + ko] = A.normalize ? fminf(fmaxf(fmaf(d, lin_scale, lin_shift), 0.0f), 1.0f) : d;
+            }
+          }
+        };
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int sa = j < 8 ? j : 8 + j;                      // lane 0's own pairs
+          const int sb = j == 0 ? 0 : (j < 8 ? 16 - j : 39 - j);
+          const T zr = (j >= 8 && hl == 0) ? re[sa] : re[j];
+          const T zi = (j >= 8 && hl == 0) ? im[sa] : im[j];
+          const T pr = __shfl_sync(0xffffffffu, hl == 0 ? re[sb] : re[31 - j], partner);
+          const T pi = __shfl_sync(0xffffffffu, hl == 0 ? im[sb] : im[31 - j], partner);
+          const int k = hl != 0 ? hl + 32 * j : (j < 8 ? 32 * j : 32 * j - 240);
+          const int kn = 512 - k;
+          const C w = s_w2k[k];                                  // exp(-2 pi i k / 1024)
+          const T er = zr + pr, ei = zi - pi;                    // Zk + conj Zn
+          const T dr = zr - pr, di = zi + pi;                    // Zk - conj Zn
+          const T wor = w.x * di + w.y * dr;
+          const T woi = w.y * di - w.x * dr;
+          if (live) {
+            emit(k, er + wor, ei + woi);                         // 2 X[k]
+            emit(kn, er - wor, woi - ei);                        // 2 X[512 - k]
+          }
+        }
+        if (hl == 0 && live) emit(256, T(2) * re[8], T(-2) * im[8]);     // self-conjugate bin: X = conj(Z)
+        if (FAST) {
+          s_mag[513 + hl] = 0.0f;                                // zero slack read (times zero weights) by padded filters
+          __syncwarp();
+          for (int f = 0; f < 2 && 2 * jp + f < FT; ++f) {
+            const float* smf = s_mag2 + f * HMAG;
+            float* mel_row = A.mel_out ? A.mel_out + (r0 + a + 2 * jp + f) * A.n_mels : nullptr;
+            for (int j = 0; j < A.melp_slots; ++j) {
+              const int m = A.melp_mbase[j] + lane;
+              const bool valid = m >= 0 && m < A.n_mels;
+              const float2* wp = reinterpret_cast<const float2*>(s_melp_w) + A.melp_woff[j] + lane;
+              const float2* mg = reinterpret_cast<const float2*>(smf + (valid ? s_mel_k0[m] : 0));
+              const int len = A.melp_len[j];
+              float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 4
+              for (int i = 0; i < len; ++i) {
+                const float2 w = wp[32 * i], v = mg[i];
+                acc0 = fmaf(w.x, v.x, acc0);
+                acc1 = fmaf(w.y, v.y, acc1);
+              }
+              const float m2 = acc0 + acc1;                      // 2 x mel
+              if (valid) {
+                mmin = fminf(mmin, m2);
+                mmax = fmaxf(mmax, m2);
+                if (mel_row) mel_row[m] = fminf(fmaxf(fmaf(sstts_log2_ftz(fmaxf(2e-5f, m2)), fm_a, fm_b), clip_lo), clip_hi);
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        __syncwarp();
+        if (want_mel) {
+          for (int f = 0; f < 2 && 2 * jp + f < FT; ++f) {
+            const long long frow = r0 + a + 2 * jp + f;
+            const float* smf = s_mag2 + f * HMAG;
+            for (int m = lane; m < A.n_mels; m += 32) {
+              const int p0 = s_mel_ptr[m], p1 = s_mel_ptr[m + 1];
+              const float* mg = smf + s_mel_k0[m] - p0;
+              T acc = T(0);
+              if (pmode == 0) {
+                for (int i = p0; i < p1; ++i) acc += s_mel_w[i] * (T)mg[i];
+              } else if (pmode == 1) {
+                for (int i = p0; i < p1; ++i) acc += s_mel_w[i] * (T)(mg[i] * mg[i]);
+              } else {
+                for (int i = p0; i < p1; ++i) acc += s_mel_w[i] * (T)powf(mg[i], A.mel_power);
+              }
+              if (A.melraw_out) A.melraw_out[frow * A.n_mels + m] = (double)acc;
+              const float db = kDbPerLog2Mag * sstts_log2_approx(fmaxf(1e-5f, fabsf((float)acc)));
+              mn_mel = fminf(mn_mel, db);
+              mx_mel = fmaxf(mx_mel, db);
+              if (A.mel_out)
+                A.mel_out[frow * A.n_mels + m] = A.normalize ? fminf(fmaxf(fmaf(db, mel_scale, mel_shift), 0.0f), 1.0f) : db;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (FAST) {
+        // 20 log10(max(1e-5, |X|)) from 4 |X|^2, 20 log10(max(1e-5, mel)) from 2 mel (audio/conversion.py:29)
+        mn_lin = kDbPerLog2Pow * (sstts_log2_ftz(fmaxf(4e-10f, pmin)) - 2.0f);
+        mx_lin = kDbPerLog2Pow * (sstts_log2_ftz(fmaxf(4e-10f, pmax)) - 2.0f);
+        mn_mel = kDbPerLog2Mag * (sstts_log2_ftz(fmaxf(2e-5f, mmin)) - 1.0f);
+        mx_mel = kDbPerLog2Mag * (sstts_log2_ftz(fmaxf(2e-5f, mmax)) - 1.0f);
+      }
+    }
+    if constexpr (!G::kNative1024)
     for (int jr = warp; jr < FT; jr += W) {
       const long long row = r0 + a + jr;
       T re[32], im[32];
@@ -1103,7 +1276,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
         mn_mel = fminf(mn_mel, __shfl_xor_sync(0xffffffffu, mn_mel, o));
         mx_mel = fmaxf(mx_mel, __shfl_xor_sync(0xffffffffu, mx_mel, o));
       }
-      if (lane == 0 && warp < FT) {
+      if (lane == 0 && (G::kNative1024 ? 2 * warp < FT : warp < FT)) {
         long long* mm = A.minmax_out + 4LL * tl.clip;
         atomicMin(mm + 0, encode_ordered((double)mn_lin));
         atomicMax(mm + 1, encode_ordered((double)mx_lin));

@@ -61,7 +61,8 @@ def griffin_lim(mags, angles, n_iter, prec=0, win=1102, hop=275, want_mse=False,
 
 def stft_features(wavs, prec=1, r=1, n_fft=2048, win=1102, hop=275, sr=22050, n_mels=80, fmin=0.,
                   fmax=8000., normalize=None, power=1.0, grid_cap=3, fast=False):
-    """fast=True requests only lin + mel dB, which selects the kernel's fused dB-feature mode."""
+    """fast=True requests only lin + mel dB (n_fft 1024: + the per-clip extrema), which selects the kernel's
+    fused float32-epilogue mode."""
     nb = n_fft // 2 + 1
     so = np.concatenate([[0], np.cumsum([len(w) for w in wavs])]).astype(np.int64)
     wav = np.concatenate(wavs).astype(np.float32)
@@ -78,7 +79,7 @@ def stft_features(wavs, prec=1, r=1, n_fft=2048, win=1102, hop=275, sr=22050, n_
                                 so.ctypes.data_as(_lp), r, wav.ctypes.data_as(_fp),
                                 None if fast else spec.view(np.float32).ctypes.data_as(_fp), lin.ctypes.data_as(_fp),
                                 mel.ctypes.data_as(_fp), None if fast else melraw.ctypes.data_as(_dp),
-                                None if fast else mm.ctypes.data_as(_dp),
+                                None if (fast and n_fft != 1024) else mm.ctypes.data_as(_dp),
                                 int(normalize is not None), *consts, power, grid_cap, int(fast))
     assert rc == 0
     return [dict(spec=spec[ro[i]:ro[i + 1]], lin=lin[ro[i]:ro[i + 1]], mel=mel[ro[i]:ro[i + 1]],

@@ -26,9 +26,10 @@ template <typename T> struct HostTables {
     StftTables<T> t; t.tw1024 = tw.data(); t.w2048 = w2.data(); t.window = win.data(); return t;
   }
 };
-template <typename T> void fill_tables(int win, HostTables<T>& H) {
+template <typename T> void fill_tables(int win, HostTables<T>& H, bool native1024 = false) {
   std::vector<double> tw, w2, wn;
-  make_tables(win, tw, w2, wn);
+  if (native1024) make_tables_native1024(win, tw, w2, wn);
+  else make_tables(win, tw, w2, wn);
   H.tw.resize(1024); H.w2.resize(1024); H.win.resize(win);
   for (int i = 0; i < 1024; ++i) {
     H.tw[i].x = (T)tw[2 * i]; H.tw[i].y = (T)tw[2 * i + 1];
@@ -111,19 +112,20 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   std::string err;
   std::vector<long long> cs(n_clips), cl(n_clips);
   for (int c = 0; c < n_clips; ++c) { cs[c] = sample_off[c]; cl[c] = sample_off[c + 1] - sample_off[c]; }
-  if (!build_feat_plan(n_clips, cs.data(), cl.data(), n_fft, win, hop, reduction, H, err)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
+  if (!build_feat_plan(n_clips, cs.data(), cl.data(), n_fft, win, hop, reduction, H, err, sizeof(T) == 8)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
   HostTables<T> tabs;
-  fill_tables<T>(win, tabs);
+  fill_tables<T>(win, tabs, G::kNative1024);
   MelCSR M;
   std::vector<T> mw;
   MelPadded MP;
   if (n_mels > 0) {
     make_mel_csr(sr, n_fft, n_mels, fmin, fmax > 0 ? fmax : sr / 2.0, M);
     mw.assign(M.w.begin(), M.w.end());
-    make_mel_padded(M, n_mels, FEAT_PLANE_ELEMS, MP);
+    make_mel_padded(M, n_mels, G::kNative1024 ? HMAG : FEAT_PLANE_ELEMS, MP);
   }
   // same selection rule as sstts.cu:run_features
-  const bool fast = fast_mode && MP.ok && n_fft == NFFT && lin && mel && !spec && !melraw && !minmax && power == 1.0;
+  const bool fast = fast_mode && MP.ok && !spec && !melraw && power == 1.0 &&
+                    (G::kNative1024 ? (lin || mel || minmax) : (n_fft == NFFT && lin && mel && !minmax));
   if (fast_mode && !fast) { fprintf(stderr, "dB-feature mode does not apply to this request\n"); return -2; }
   std::vector<long long> mm(4 * (size_t)n_clips);
   FeatArgs<T> A;
@@ -193,11 +195,13 @@ int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels,
 #define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap, fast_mode
   if (prec == 1) {
     if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, kFeatWarpsF64>(FEAT_ARGS);
-    if (stats) return emu_feat_run<double, StaticGeom<1024, 256, 1024>, kFeatWarpsF64>(FEAT_ARGS);
+    if (stats) return emu_feat_run<double, NativeGeom1024<1024, 256>, kFeatWarpsF64>(FEAT_ARGS);
+    if (feat_native_1024(n_fft)) return emu_feat_run<double, DynGeom1024, kFeatWarpsF64>(FEAT_ARGS);
     return emu_feat_run<double, DynGeom, kFeatWarpsF64>(FEAT_ARGS);
   }
   if (model) return emu_feat_run<float, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);
-  if (stats) return emu_feat_run<float, StaticGeom<1024, 256, 1024>, kWarps>(FEAT_ARGS);
+  if (stats) return emu_feat_run<float, NativeGeom1024<1024, 256>, kWarps>(FEAT_ARGS);
+  if (feat_native_1024(n_fft)) return emu_feat_run<float, DynGeom1024, kWarps>(FEAT_ARGS);
   return emu_feat_run<float, DynGeom, kWarps>(FEAT_ARGS);
 #undef FEAT_ARGS
 }

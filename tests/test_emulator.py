@@ -156,17 +156,58 @@ def test_feature_pipeline_fused_db_mode(emu, prec, tol_lin, normalize):
             assert np.abs(f['mel'] - mel_ref.reshape(-1, 80)).max() < 3e-6
 
 
-def test_decibel_statistics_geometry(emu):
-    """datasets/statistics.py:31-51: n_fft 1024 / hop 256 / win 1024, fmax sr//2, embedded in the
-    2048-point transform (every other bin)."""
+@pytest.mark.parametrize('prec,tol', [(1, 1e-7), (0, 1e-6)])
+def test_decibel_statistics_geometry(emu, prec, tol):
+    """datasets/statistics.py:31-51: n_fft 1024 / hop 256 / win 1024, fmax sr//2 -- the feature kernel's
+    NATIVE n_fft 1024 path (512-point complex transform on half a warp, two frames per warp, 16-frame
+    tiles): single-frame clips, odd and even tile sizes, several tiles per clip."""
     rng = np.random.default_rng(9)
-    wavs = [speech_like_clip(n, rng) for n in (300, 5000, 22050)]
-    res = emu.stft_features(wavs, prec=1, n_fft=1024, win=1024, hop=256, fmax=11025.)
+    wavs = [speech_like_clip(max(n, 8), rng)[:n] for n in (1, 255, 300, 256 * 2, 5000, 256 * 16 + 5, 22050)]
+    res = emu.stft_features(wavs, prec=prec, n_fft=1024, win=1024, hop=256, fmax=11025.)
     for w, r in zip(wavs, res):
         S = lc.stft(w, 1024, 256, 1024).T
         assert r['spec'].shape == S.shape
-        assert np.abs(r['spec'] - S).max() / np.abs(S).max() < 1e-7
-        assert np.abs(r['minmax'] - ra.decibel_statistics(w, 22050)).max() < 2e-5
+        assert np.abs(r['spec'] - S).max() / np.abs(S).max() < tol
+        if prec == 1:
+            assert np.abs(r['minmax'] - ra.decibel_statistics(w, 22050)).max() < 2e-5
+            mr = ra.mel_scale_spectrogram(w, 1024, 22050, 80, 0, 11025, 256, 1024, 1).T
+            assert np.abs(r['melraw'] - mr).max() / np.abs(mr).max() < 1e-6
+            lin_db = ra.magnitude_to_decibel(np.abs(S))
+            assert np.abs(r['lin'] - lin_db).max() < 2e-4
+
+
+@pytest.mark.parametrize('prec', [1, 0])
+def test_statistics_fused_mode(emu, prec):
+    """The statistics request (per-clip extrema, optionally linear / mel dB) runs the native path's fused
+    float32 epilogue: extrema of the dB values taken as dB of the extrema, mel sums in float32."""
+    rng = np.random.default_rng(29)
+    wavs = [speech_like_clip(max(n, 8), rng)[:n] for n in (1, 300, 256 * 3, 5000, 256 * 16 + 5, 22050)]
+    wavs.append(np.zeros(3000, np.float32))                          # digital silence: the -100 dB floor
+    fast = emu.stft_features(wavs, prec=prec, n_fft=1024, win=1024, hop=256, fmax=11025., fast=True)
+    slow = emu.stft_features(wavs, prec=prec, n_fft=1024, win=1024, hop=256, fmax=11025.)
+    for w, f, g in zip(wavs, fast, slow):
+        assert np.abs(f['minmax'] - g['minmax']).max() < 1e-4        # dB
+        assert np.abs(f['lin'] - g['lin']).max() < 3e-4 and np.abs(f['mel'] - g['mel']).max() < 3e-4
+        if prec == 1:
+            assert np.abs(f['minmax'] - ra.decibel_statistics(w, 22050)).max() < 1e-4
+
+
+def test_native_1024_transform_with_a_shorter_window(emu):
+    """n_fft 1024 with win < n_fft (window centred with zero padding) and a hop that is not win / 4:
+    the run-time geometry instance of the native path; normalised dB outputs and reduction padding."""
+    rng = np.random.default_rng(19)
+    wavs = [speech_like_clip(n, rng) for n in (777, 6000, 15000)]
+    consts = (35.66, 100.0, 6.02, 99.89)
+    res = emu.stft_features(wavs, prec=1, r=5, n_fft=1024, win=800, hop=200, fmax=8000., normalize=consts)
+    for w, r in zip(wavs, res):
+        S = lc.stft(w, 1024, 200, 800).T
+        T = S.shape[0]
+        assert r['T'] == T and np.abs(r['spec'][:T] - S).max() / np.abs(S).max() < 1e-7
+        lin = ra.normalize_decibel(ra.magnitude_to_decibel(np.abs(S)), consts[0], consts[1])
+        mel = ra.mel_scale_spectrogram(w, 1024, 22050, 80, 0, 8000, 200, 800, 1).T
+        mel = ra.normalize_decibel(ra.magnitude_to_decibel(np.abs(mel)), consts[2], consts[3])
+        assert np.abs(r['lin'][:T] - lin).max() < 2e-6 and np.abs(r['mel'][:T] - mel).max() < 2e-6
+        assert np.all(r['lin'][T:] == 0) and np.all(r['mel'][T:] == 0)
 
 
 def test_mel_basis_matches_oracle(emu):
