@@ -28,6 +28,7 @@ constexpr int kWarps = SSTTS_WARPS;
 #define SSTTS_FEAT_WARPS_F64 4
 #endif
 constexpr int kFeatWarpsF64 = SSTTS_FEAT_WARPS_F64;
+constexpr int kFeatWarpsF64Native = 4;   // native n_fft 1024 path in float64: two frames per warp, 8-frame tiles
 #ifndef SSTTS_GL_WARPS
 #define SSTTS_GL_WARPS 8
 #endif
@@ -119,9 +120,12 @@ inline bool feat_native_1024(int n_fft) { return n_fft == 1024; }
 // Frames per tile: one frame per warp and round (kTileFrames), or -- native n_fft 1024 path -- two frames per
 // warp of the CTA (float32: 8 warps, float64: kFeatWarpsF64 warps; a larger tile would push the float64
 // kernel's sample buffers past the shared memory that lets two CTAs share an SM).
+#ifndef SSTTS_FEAT_TILE_F64
+#define SSTTS_FEAT_TILE_F64 SSTTS_WARPS
+#endif
 inline int feat_tile_frames(int n_fft, bool f64) {
-  if (!feat_native_1024(n_fft)) return kTileFrames;
-  const int t = 2 * (f64 ? kFeatWarpsF64 : kWarps);
+  if (!feat_native_1024(n_fft)) return f64 ? SSTTS_FEAT_TILE_F64 : kTileFrames;
+  const int t = 2 * (f64 ? kFeatWarpsF64Native : kWarps);
   return t < kNativeTileFrames ? t : kNativeTileFrames;
 }
 

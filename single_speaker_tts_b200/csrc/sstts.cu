@@ -608,7 +608,7 @@ int run_features(const sstts_feat_plan* P, const float* wav, const sstts_feat_ou
   for (int j = 0; j < 4; ++j) { A.melp_len[j] = S.melp.len[j]; A.melp_woff[j] = S.melp.woff[j]; A.melp_mbase[j] = S.melp.mbase[j]; }
 
   const size_t smem = stft_feature_smem_bytes<T>(W, H.win, H.span_max, P->cfg.n_mels, (int)S.mel.w.size(),
-                                                 A.melp_total);
+                                                 A.melp_total, feat_plane_elems<G>());
   auto kernel = fast ? stft_feature_kernel<T, G, W, FeatMode::kDbFeatures>
                      : stft_feature_kernel<T, G, W, FeatMode::kGeneric>;
   int occ = 0, rc;
@@ -852,8 +852,8 @@ int sstts_stft_features(const sstts_feat_plan* P, const float* wav_dev, const ss
   const bool native = feat_native_1024(P->cfg.n_fft);
   if (P->cfg.precision == SSTTS_F64) {
     if (model) return run_features<double, ModelGeom, kFeatWarpsF64>(P, wav_dev, out, st);
-    if (stats) return run_features<double, StatsGeom, kFeatWarpsF64>(P, wav_dev, out, st);
-    if (native) return run_features<double, DynGeom1024, kFeatWarpsF64>(P, wav_dev, out, st);
+    if (stats) return run_features<double, StatsGeom, kFeatWarpsF64Native>(P, wav_dev, out, st);
+    if (native) return run_features<double, DynGeom1024, kFeatWarpsF64Native>(P, wav_dev, out, st);
     return run_features<double, DynGeom, kFeatWarpsF64>(P, wav_dev, out, st);
   }
   if (model) return run_features<float, ModelGeom, kWarps>(P, wav_dev, out, st);

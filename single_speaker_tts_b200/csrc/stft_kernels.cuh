@@ -849,7 +849,11 @@ SSTTS_D long long encode_ordered(double v) {
 #define kDbPerLog2Mag 6.020599913279624f
 #define kDbPerLog2Pow 3.010299956639812f
 
-constexpr int FEAT_PLANE_ELEMS = 1120;  // >= XPLANE_ELEMS, >= NBINS floats and >= 2 * HPLANE_ELEMS
+constexpr int FEAT_PLANE_ELEMS = 1056;         // per-warp plane: >= XPLANE_ELEMS and >= NBINS floats
+constexpr int FEAT_PLANE_ELEMS_NATIVE = 1120;  // native n_fft 1024 path: >= 2 * HPLANE_ELEMS (and 2 * HMAG floats)
+template <typename G> SSTTS_HD constexpr int feat_plane_elems() {
+  return G::kNative1024 ? FEAT_PLANE_ELEMS_NATIVE : FEAT_PLANE_ELEMS;
+}
 constexpr int kNativeTileFrames = 16;   // frames per tile of the native n_fft 1024 path (two per warp and round)
 constexpr int HMAG = 544;               // per-half |S| row of the native path: 513 bins + zero slack for padded filters
 
@@ -866,7 +870,7 @@ struct FeatMode { enum { kGeneric = 0, kDbFeatures = 1 }; };
 #define SSTTS_FEAT_MINBLOCKS 2
 #endif
 template <typename T, typename G, int W, int MODE>
-__global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS : (W <= 4 ? 2 : 1)) stft_feature_kernel(const FeatArgs<T> A) {
+__global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS : (W <= 6 ? 2 : 1)) stft_feature_kernel(const FeatArgs<T> A) {
   constexpr bool FAST = MODE == FeatMode::kDbFeatures;
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, A.n_fft);
@@ -880,8 +884,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = s_tw + 1024;
   T* s_planes = reinterpret_cast<T*>(s_w2k + 512);
-  T* s_win = load_window_table<T>(s_planes + W * FEAT_PLANE_ELEMS, A.tab.window, win, lpad, tid, W * 32);
-  float* s_x = reinterpret_cast<float*>(s_planes + W * FEAT_PLANE_ELEMS + round_up4(win + WIN_TAB_PAD));
+  constexpr int PLANE = feat_plane_elems<G>();
+  T* s_win = load_window_table<T>(s_planes + W * PLANE, A.tab.window, win, lpad, tid, W * 32);
+  float* s_x = reinterpret_cast<float*>(s_planes + W * PLANE + round_up4(win + WIN_TAB_PAD));
 
   for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
@@ -905,7 +910,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   }
   __syncthreads();
 
-  T* plane = s_planes + warp * FEAT_PLANE_ELEMS;
+  T* plane = s_planes + warp * PLANE;
   const bool want_lin = A.lin_out != nullptr;
   const bool want_lin_db = want_lin || (A.minmax_out != nullptr);
   const bool want_mel = (A.n_mels > 0) && ((A.mel_out != nullptr) || (A.melraw_out != nullptr) ||
@@ -1291,12 +1296,12 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
 // melp_total > 0 (weight pairs) selects the dB-feature layout (padded float2 table + k0) instead of the CSR one.
 template <typename T>
 SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_mels, int mel_nnz,
-                                        int melp_total = 0) {
+                                        int melp_total = 0, int plane_elems = FEAT_PLANE_ELEMS) {
   const size_t mel = melp_total > 0
       ? sizeof(float) * (size_t)round_up4(2 * melp_total) + sizeof(int) * (size_t)round_up4(n_mels)
       : sizeof(T) * (size_t)round_up4(mel_nnz) + sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
   return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
-         sizeof(T) * (size_t)(warps * FEAT_PLANE_ELEMS + round_up4(win + WIN_TAB_PAD)) +
+         sizeof(T) * (size_t)(warps * plane_elems + round_up4(win + WIN_TAB_PAD)) +
          sizeof(float) * 2 * (size_t)(round_up4(span_max) + 8) + mel;
 }
 

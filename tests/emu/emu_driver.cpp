@@ -142,7 +142,8 @@ int emu_feat_run(int n_fft, int win, int hop, int sr, int n_mels, double fmin, d
   A.melp_w = MP.w.data(); A.melp_slots = fast ? MP.n_slots : 0; A.melp_total = fast ? MP.total : 0;
   for (int j = 0; j < 4; ++j) { A.melp_len[j] = MP.len[j]; A.melp_woff[j] = MP.woff[j]; A.melp_mbase[j] = MP.mbase[j]; }
   if (minmax) for (size_t i = 0; i < mm.size(); ++i) mm[i] = (i & 1) ? encode_ordered(-1e300) : encode_ordered(1e300);
-  const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max, n_mels, (int)mw.size(), A.melp_total);
+  const size_t smem = stft_feature_smem_bytes<T>(W, win, H.span_max, n_mels, (int)mw.size(), A.melp_total,
+                                                 feat_plane_elems<G>());
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
   if (fast) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { stft_feature_kernel<T, G, W, FeatMode::kDbFeatures>(A); });
   else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { stft_feature_kernel<T, G, W, FeatMode::kGeneric>(A); });
@@ -195,8 +196,8 @@ int emu_stft_features(int n_fft, int win, int hop, int prec, int sr, int n_mels,
 #define FEAT_ARGS n_fft, win, hop, sr, n_mels, fmin, fmax, n_clips, sample_off, reduction, wav, spec, lin, mel, melraw, minmax, normalize, lin_ref, lin_max, mel_ref, mel_max, power, grid_cap, fast_mode
   if (prec == 1) {
     if (model) return emu_feat_run<double, StaticGeom<1102, 275, 2048>, kFeatWarpsF64>(FEAT_ARGS);
-    if (stats) return emu_feat_run<double, NativeGeom1024<1024, 256>, kFeatWarpsF64>(FEAT_ARGS);
-    if (feat_native_1024(n_fft)) return emu_feat_run<double, DynGeom1024, kFeatWarpsF64>(FEAT_ARGS);
+    if (stats) return emu_feat_run<double, NativeGeom1024<1024, 256>, kFeatWarpsF64Native>(FEAT_ARGS);
+    if (feat_native_1024(n_fft)) return emu_feat_run<double, DynGeom1024, kFeatWarpsF64Native>(FEAT_ARGS);
     return emu_feat_run<double, DynGeom, kFeatWarpsF64>(FEAT_ARGS);
   }
   if (model) return emu_feat_run<float, StaticGeom<1102, 275, 2048>, kWarps>(FEAT_ARGS);

@@ -17,6 +17,7 @@ from single_speaker_tts_b200.synthetic import make_clips      # noqa: E402
 
 n_iter = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 n_utts = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+REPS = 1 if os.environ.get('PROF_ONCE') else 2      # under ncu every launch is replayed anyway
 WIN, HOP, NFFT = 1102, 275, 2048
 clips = make_clips(n_utts, seed=1, pool=16)
 mags = []
@@ -26,17 +27,24 @@ off = np.concatenate([[0], np.cumsum(fb.frames)])
 mags = [mag[off[i]:off[i + 1]].T for i in range(n_utts)]
 _runtime._GL_CHUNK_FRAMES = 10 ** 9      # whole batch in one launch sequence, like bench.py's device-resident `value`
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for rep in range(2):
+for rep in range(REPS):
     e0.record()
     wavs = _runtime.griffin_lim_batch(mags, WIN, HOP, NFFT, n_iter, seed=3)[0]
     e1.record(); torch.cuda.synchronize()
     print('gl e2e n_iter', n_iter, 'ms', e0.elapsed_time(e1))
 for prec in ('f32', 'f64'):
-    for rep in range(2):
+    for rep in range(REPS):
         e0.record()
         r = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, sampling_rate=22050, n_mels=80, fmin=0, fmax=8000,
                                          reduction=5, want_lin=True, want_mel=True, normalize=(35.66, 100.0, 6.02, 99.89),
                                          precision=prec, keep_on_device=True)
         e1.record(); torch.cuda.synchronize()
         print('features', prec, 'ms', e0.elapsed_time(e1))
+for prec in ('f64', 'f32'):
+    for rep in range(REPS):
+        e0.record()
+        r = _runtime.stft_features_batch(clips, 1024, 256, 1024, sampling_rate=22050, n_mels=80, fmin=0, fmax=11025,
+                                         want_minmax=True, precision=prec, keep_on_device=True)
+        e1.record(); torch.cuda.synchronize()
+        print('statistics', prec, 'ms', e0.elapsed_time(e1))
 print('ok')
