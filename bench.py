@@ -318,6 +318,11 @@ class Harness:
         if self.world > 1:
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
             dist.init_process_group('nccl', device_id=self.dev)
+        # one process per GPU on a shared host: the ranks split the cores for the (memory-bound) host-side packing
+        import single_speaker_tts_b200 as pkg
+        cores = len(os.sched_getaffinity(0))
+        self.io_threads = max(2, min(8, cores // self.world))
+        pkg.set_io_threads(self.io_threads)
 
     def close(self):
         if self.world > 1:
@@ -565,6 +570,7 @@ def bench_primary(H, args):
         'gpu_launches': args.steps * (GL_ITERS + 2),
         'roofline': roofline,
         'clocks': clocks,
+        'host': {'cores': len(os.sched_getaffinity(0)), 'io_threads_per_rank': H.io_threads},
         'features': {'metric': 'feature_audio_sec_per_sec',
                      'workload': 'BASELINE configs[1]: STFT -> linear + 80-mel dB-normalised features, '
                                  '256 ragged clips per GPU',
@@ -638,7 +644,8 @@ def bench_corpus(H, args, n_total=13100):
     state = {}
 
     def one_pass():
-        mean4, n_rows = distributed.corpus_pass(wavs, mine, n_total, SR, NFFT, HOP, WIN, 80, 0, 8000, reduction=5)
+        mean4, n_rows = distributed.corpus_pass(wavs, mine, n_total, SR, NFFT, HOP, WIN, 80, 0, 8000, reduction=5,
+                                                chunk_samples=args.corpus_chunk)
         state['mean4'], state['rows'] = mean4, n_rows
 
     steps = max(1, min(args.steps, 2))
@@ -731,6 +738,7 @@ def main():
                     help='all = the driver contract line with every sub-result (default); gl256 = configs[1]+[2] '
                          'only; corpus = configs[3]; gl4096 = configs[4]; latency = single utterance')
     ap.add_argument('--clips', type=int, default=0, help='override the clip count of corpus / gl4096')
+    ap.add_argument('--corpus-chunk', type=int, default=16 << 20, help='samples per device batch of the corpus pass')
     ap.add_argument('--ref-items', type=int, default=0,
                     help='--impl reference: utterances per step (default 2 x host cores)')
     args = ap.parse_args()

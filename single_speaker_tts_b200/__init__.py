@@ -7,3 +7,9 @@ def pinned_empty(shape, dtype='float32'):
     import numpy as np
     from . import _hostio
     return _hostio.pinned_empty(shape, np.dtype(dtype))
+
+
+def set_io_threads(n):
+    """Host threads used to pack ragged batches into pinned staging buffers (see ``_hostio.set_io_threads``)."""
+    from . import _hostio
+    _hostio.set_io_threads(n)

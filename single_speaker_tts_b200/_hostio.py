@@ -28,6 +28,20 @@ _executor = None
 _executor_lock = threading.Lock()
 
 
+def set_io_threads(n):
+    """Number of host threads that pack ragged batches into the pinned staging buffers (default 8).  With one
+    process per GPU on a shared host use about ``cores // world_size``: the packing is memory-bound and
+    more threads than that only fight over the same memory channels."""
+    global _N_WORKERS, _executor
+    n = max(1, int(n))
+    with _executor_lock:
+        if n != _N_WORKERS:
+            _N_WORKERS = n
+            if _executor is not None:
+                _executor.shutdown(wait=True)
+                _executor = None
+
+
 def _pool():
     global _executor
     if _executor is None:

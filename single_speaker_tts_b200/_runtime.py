@@ -105,7 +105,7 @@ class _PlanCache:
     parked and only released by :meth:`reap`, which the batch entry points call after their final
     synchronisation -- an eviction in the middle of a sub-batch pipeline would stall it."""
 
-    def __init__(self, capacity=64):
+    def __init__(self, capacity=2048):
         self._cap = capacity
         self._d = collections.OrderedDict()
         self._dead = []
@@ -540,7 +540,7 @@ def stft_features_batch(wavs, n_fft, hop_length, win_length, sampling_rate=None,
     row_off = np.ctypeslib.as_array(lib.sstts_feat_row_offsets(plan.handle), shape=(n + 1,)).copy()
     res = FeatureBatch(n, [int(frame_off[i + 1] - frame_off[i]) for i in range(n)], row_off, reduction)
     res.trim_bounds = trim_bounds
-    if need_mel and cfg.n_mels > 0:
+    if want_mel_raw and cfg.n_mels > 0:          # the filterbank itself, for callers of mel_scale_spectrogram
         res.mel_basis = np.ctypeslib.as_array(lib.sstts_feat_mel_basis(plan.handle),
                                               shape=(cfg.n_mels, n_bins)).copy()
 

@@ -639,3 +639,31 @@ def test_peak_normalisation_matches_save_wav_norm():
         assert abs(float(np.max(np.abs(n))) - 1.0) < 1e-6
     z = synthesis.spectrograms_to_wavs([np.zeros((1025, 6), np.float32)], WIN, HOP, NFFT, 1, seed=1, normalize_peak=True)
     assert np.array_equal(z[0], np.zeros(HOP * 5, np.float32))
+
+
+def test_corpus_pass_equals_the_two_separate_drivers():
+    """BASELINE configs[3] on one rank: distributed.corpus_pass (one upload, statistics kernel, reduction,
+    pre-calculation on the resident clips, pipelined downloads) must produce exactly the statistics of
+    collect_decibel_statistics_from_wavs and, with them as constants, exactly the features of features_batch
+    -- also when the shard is split into several device batches."""
+    from single_speaker_tts_b200 import distributed
+    rng = np.random.default_rng(91)
+    clips = [speech_like_clip(int(n), rng) for n in (9000, 300, 22050, 5000, 14000, 275, 31000, 1200)]
+    idx = list(range(len(clips)))
+    want_stats = statistics.collect_decibel_statistics_from_wavs(clips, 22050)
+    lin_max, lin_ref, mel_max, mel_ref = want_stats
+    want = features.features_batch(clips, NFFT, HOP, WIN, 22050, 80, 0, 8000, lin_ref, lin_max, mel_ref, mel_max, reduction=5)
+    for chunk in (1 << 30, 20000):
+        got = {}
+
+        def sink(indices, part):
+            for j, i in enumerate(indices):
+                got[i] = (part.rows(part.mel_db, j, padded=True).reshape(-1, 400).copy(),
+                          part.rows(part.lin_db, j, padded=True).reshape(-1, 5125).copy())
+
+        mean4, n_rows = distributed.corpus_pass(clips, idx, len(clips), 22050, NFFT, HOP, WIN, 80, 0, 8000,
+                                                reduction=5, chunk_samples=chunk, sink=sink)
+        assert np.array_equal(mean4, want_stats)
+        assert n_rows == sum(m.shape[0] * 5 for m, _ in want)
+        for i, (mel, lin) in enumerate(want):
+            assert np.array_equal(got[i][0], mel) and np.array_equal(got[i][1], lin)
