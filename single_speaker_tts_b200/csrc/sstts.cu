@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -364,7 +365,14 @@ const int64_t* sstts_gl_sample_offsets(const sstts_gl_plan* P) {
 
 namespace {
 
-template <typename T, typename G, int W>
+// SSTTS_GL_STAGING=bulk selects the iteration kernel whose interior tiles are staged with bulk asynchronous
+// copies (see GLSmem in stft_kernels.cuh for the A/B); read once per process.
+bool gl_bulk_requested() {
+  static const bool v = [] { const char* e = getenv("SSTTS_GL_STAGING"); return e && std::string(e) == "bulk"; }();
+  return v;
+}
+
+template <typename T, typename G, int W, bool BULK>
 int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase0, uint64_t seed,
                     int64_t first, int n_iter, void* workspace, float* wav_out, double* mse_frame,
                     cudaStream_t st) {
@@ -385,11 +393,11 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   A.mse_frame = nullptr;
   A.win = H.win; A.hop = H.hop; A.span_max = H.span_max; A.n_fft = H.n_fft;
 
-  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.hop, H.span_max);
+  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.hop, H.span_max, BULK);
   int occ_s = 0, occ_i = 0, occ_m = 0, rc;
-  if ((rc = configure_kernel(gl_step_kernel<T, G, W, true, false>, W * 32, smem, &occ_s))) return rc;
-  if ((rc = configure_kernel(gl_step_kernel<T, G, W, false, false>, W * 32, smem, &occ_i))) return rc;
-  if (mse_frame && (rc = configure_kernel(gl_step_kernel<T, G, W, false, true>, W * 32, smem, &occ_m))) return rc;
+  if ((rc = configure_kernel(gl_step_kernel<T, G, W, true, false, BULK>, W * 32, smem, &occ_s))) return rc;
+  if ((rc = configure_kernel(gl_step_kernel<T, G, W, false, false, BULK>, W * 32, smem, &occ_i))) return rc;
+  if (mse_frame && (rc = configure_kernel(gl_step_kernel<T, G, W, false, true, BULK>, W * 32, smem, &occ_m))) return rc;
   const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
   int grid_s = n_sms * occ_s, grid_i = n_sms * occ_i;
   if (grid_s > A.n_tiles) grid_s = A.n_tiles;
@@ -397,7 +405,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
 
   // step 0: random phase -> wave_1 (written to buf[0], buf[1])
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
-  gl_step_kernel<T, G, W, true, false><<<grid_s, W * 32, smem, st>>>(A);
+  gl_step_kernel<T, G, W, true, false, BULK><<<grid_s, W * 32, smem, st>>>(A);
   CU(cudaGetLastError());
   int cur = 0;
   for (int it = 0; it < n_iter; ++it) {
@@ -407,9 +415,9 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
       A.mse_frame = mse_frame;
       int grid_m = n_sms * occ_m;
       if (grid_m > A.n_tiles) grid_m = A.n_tiles;
-      gl_step_kernel<T, G, W, false, true><<<grid_m, W * 32, smem, st>>>(A);
+      gl_step_kernel<T, G, W, false, true, BULK><<<grid_m, W * 32, smem, st>>>(A);
     } else {
-      gl_step_kernel<T, G, W, false, false><<<grid_i, W * 32, smem, st>>>(A);
+      gl_step_kernel<T, G, W, false, false, BULK><<<grid_i, W * 32, smem, st>>>(A);
     }
     CU(cudaGetLastError());
     cur ^= 1;
@@ -645,10 +653,12 @@ static int griffin_lim_dispatch(const sstts_gl_plan* P, const float* mag_dev, co
     return fail(SSTTS_ERR_INVALID, "workspace_dev must be 16-byte aligned (bulk copies read it in 16-byte units)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
-#define GL_CALL(T, G, W) run_griffin_lim<T, G, W>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \
-                                                  wav_out_dev, mse_frame_dev, st)
-  if (P->cfg.precision == SSTTS_F64) return model ? GL_CALL(double, ModelGeom, kWarps) : GL_CALL(double, DynGeom, kWarps);
-  return model ? GL_CALL(float, ModelGeom, kGlWarps) : GL_CALL(float, DynGeom, kGlWarps);
+#define GL_CALL(T, G, W, B) run_griffin_lim<T, G, W, B>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \
+                                                        wav_out_dev, mse_frame_dev, st)
+  if (P->cfg.precision == SSTTS_F64)
+    return model ? GL_CALL(double, ModelGeom, kWarps, false) : GL_CALL(double, DynGeom, kWarps, false);
+  if (gl_bulk_requested()) return model ? GL_CALL(float, ModelGeom, kGlWarps, true) : GL_CALL(float, DynGeom, kGlWarps, true);
+  return model ? GL_CALL(float, ModelGeom, kGlWarps, false) : GL_CALL(float, DynGeom, kGlWarps, false);
 #undef GL_CALL
 }
 

@@ -374,32 +374,33 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)[32], c
 }
 
 // Shared-memory carve-up of the Griffin-Lim step kernel.
-// SSTTS_GL_BULK (default 1): interior tiles of the float32 iteration kernel take their input span with bulk
-// asynchronous copies (cp.async.bulk + mbarrier, the 1-D form of TMA) issued by ONE thread while the CTA is
-// still transforming the previous tile, instead of every thread loading, normalising and storing its
-// samples after the gather.  0 keeps the synchronous staging everywhere (A/B builds, tools/ab_bench.sh).
-#ifndef SSTTS_GL_BULK
-#define SSTTS_GL_BULK 1
-#endif
-template <typename T> SSTTS_HD constexpr bool gl_uses_bulk() { return SSTTS_GL_BULK != 0 && sizeof(T) == 4; }
-
+// Two staging variants of the iteration kernel (template parameter BULK of gl_step_kernel):
+//   BULK = false  every thread loads, normalises and stores its samples of the next tile after the gather
+//                 (the span was pulled into L2 by prefetch hints while the tile was being transformed);
+//   BULK = true   interior tiles take their input span with bulk asynchronous copies (cp.async.bulk +
+//                 mbarrier, the 1-D form of TMA) issued by ONE thread while the CTA is still transforming
+//                 the previous tile; the normalisation is folded into the window table.
+// Measured on B200 (profiles/experiments/r2_ab_bulk_staging.txt): 0.575 ms (bulk) vs 0.572 ms per iteration
+// launch on the 256-utterance batch, 0.916 vs 0.845 ms for one 1000-frame utterance (one tile per CTA: the
+// copy latency is exposed) -- the kernel is bound by issue slots and the shared-memory pipe, not by this
+// phase, so the library runs BULK = false unless SSTTS_GL_STAGING=bulk is set (sstts.cu).
 template <typename T> struct GLSmem {
   typedef typename cx_of<T>::type C;
   int plane_elems;   // per-warp plane: transpose tile, later the windowed output frame
   int edge_elems;    // one neighbour edge region ((win - hop) samples + alignment slack)
   size_t off_w2k, off_win, off_wr, off_rw, off_plane, off_mag, off_yin, off_edge, off_bar, total;
-  SSTTS_HD GLSmem(int warps, int win, int hop, int span_max) {
+  SSTTS_HD GLSmem(int warps, int win, int hop, int span_max, bool bulk) {
     plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
     edge_elems = round_up4(win - hop > 0 ? win - hop : 0) + 8;
     size_t o = sizeof(C) * 1024;
     off_w2k = o; o += sizeof(C) * 512;
     off_win = o; o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
-    off_wr = o; if (gl_uses_bulk<T>()) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
+    off_wr = o; if (bulk) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_rw = o; o += sizeof(T) * round_up4(hop);
     off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
     off_mag = o; o += sizeof(float) * (size_t)warps * MAGROW;
     off_yin = o; o += sizeof(T) * (round_up4(span_max) + 8);      // + slack for the 16-byte alignment shift
-    off_edge = o; if (gl_uses_bulk<T>()) o += sizeof(T) * 2 * (size_t)edge_elems;
+    off_edge = o; if (bulk) o += sizeof(T) * 2 * (size_t)edge_elems;
     off_bar = o; o += 16;                                          // mbarrier + arrival counter
     total = o;
   }
@@ -410,7 +411,7 @@ template <typename T> struct GLSmem {
 #endif
 // One Griffin-Lim step over all tiles.  FROM_PHASE = true is the initial synthesis from the
 // random phase (no analysis half).  W warps per CTA, one frame per warp, tiles of <= W frames.
-template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE>
+template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE, bool USE_BULK = false>
 __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel(const GLArgs<T> A) {
   typedef typename cx_of<T>::type C;
   const G g(A.win, A.hop, A.n_fft);
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   constexpr int NT = W * 32;
 
   SSTTS_DYN_SMEM(smem);
-  const GLSmem<T> L(W, win, hop, A.span_max);
+  const GLSmem<T> L(W, win, hop, A.span_max, USE_BULK);
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = reinterpret_cast<C*>(smem + L.off_w2k);
   T* s_win = load_window_table<T>(reinterpret_cast<T*>(smem + L.off_win), A.tab.window, win, lpad, tid, W * 32);
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   float* s_mag = reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
   T* s_yin = reinterpret_cast<T*>(smem + L.off_yin);
   T* plane = s_planes + warp * L.plane_elems;
-  constexpr bool BULK = !FROM_PHASE && gl_uses_bulk<T>();
+  constexpr bool BULK = !FROM_PHASE && USE_BULK;
   T* s_wrtab = reinterpret_cast<T*>(smem + L.off_wr);           // window x reciprocal window sum (BULK)
   T* s_wr = s_wrtab + win_shift(lpad);
   T* s_edge = reinterpret_cast<T*>(smem + L.off_edge);          // raw neighbour sums of the two edge regions
@@ -742,8 +743,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   }
 }
 
-template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int hop, int span_max) {
-  return GLSmem<T>(warps, win, hop, span_max).total;
+template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int hop, int span_max, bool bulk = false) {
+  return GLSmem<T>(warps, win, hop, span_max, bulk).total;
 }
 
 // Partial sums -> normalised, centre-trimmed float32 waveform (the reference's final istft

@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -78,19 +79,25 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   A.tiles = H.tiles.data(); A.n_tiles = (int)H.tiles.size();
   A.tab = tabs.view(); A.mse_frame = nullptr;
   A.win = win; A.hop = hop; A.span_max = H.span_max; A.n_fft = n_fft;
-  const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max);
+  // SSTTS_GL_STAGING=bulk: the bulk-copy staging variant of the float32 iteration kernel (tests run both)
+  const char* stg = getenv("SSTTS_GL_STAGING");
+  const bool bulk = sizeof(T) == 4 && stg && std::string(stg) == "bulk";
+  const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max, bulk);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
-  emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false>(A); });
+  if (bulk) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false, true>(A); });
+  else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false>(A); });
   int cur = 0;
   for (int it = 0; it < n_iter; ++it) {
     A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
     A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
     if (it == n_iter - 1 && mse_frame) {
       A.mse_frame = mse_frame;
-      emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true>(A); });
+      if (bulk) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true, true>(A); });
+      else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true>(A); });
     } else {
-      emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false>(A); });
+      if (bulk) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false, true>(A); });
+      else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false>(A); });
     }
     cur ^= 1;
   }

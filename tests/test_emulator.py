@@ -55,6 +55,23 @@ def test_griffin_lim_tiles_and_edges(emu, prec, tol):
         assert abs(mse - rmse) / rmse < 1e-5
 
 
+def test_griffin_lim_bulk_staging_variant(emu, monkeypatch):
+    """The iteration kernel's second staging variant (cp.async.bulk + mbarrier for interior tiles,
+    SSTTS_GL_STAGING=bulk): same results as the default staging up to the rounding of the folded
+    window x normalisation table, on a case with interior, first, last and reflecting tiles."""
+    frames = [2, 9, 30, 45]
+    mags, angs = _gl_case(frames)
+    monkeypatch.delenv('SSTTS_GL_STAGING', raising=False)
+    ref = emu.griffin_lim(mags, angs, 3, prec=0)
+    monkeypatch.setenv('SSTTS_GL_STAGING', 'bulk')
+    got = emu.griffin_lim(mags, angs, 3, prec=0)
+    for T, m, a, w, r in zip(frames, mags, angs, got, ref):
+        assert not np.isnan(w).any()
+        assert np.linalg.norm(w - r) / np.linalg.norm(r) < 2e-6
+        orc = ra.spectrogram_to_wav(m, WIN, HOP, NFFT, 3, angles=a, batched_fft=True)
+        assert np.linalg.norm(w - orc) / np.linalg.norm(orc) < 5e-6
+
+
 def test_griffin_lim_phase_drawn_inside_the_synthesis_launch(emu):
     """angles=None: the first launch draws unit phasors from the counter-based generator (seed fixed
     in the emulator driver).  Deterministic, finite, and a valid Griffin-Lim run: the spectrogram

@@ -667,3 +667,32 @@ def test_corpus_pass_equals_the_two_separate_drivers():
         assert n_rows == sum(m.shape[0] * 5 for m, _ in want)
         for i, (mel, lin) in enumerate(want):
             assert np.array_equal(got[i][0], mel) and np.array_equal(got[i][1], lin)
+
+
+def test_bulk_copy_staging_variant_matches_the_default(tmp_path):
+    """SSTTS_GL_STAGING=bulk runs the iteration kernel whose interior tiles are staged with cp.async.bulk +
+    mbarrier (read once per process, hence a subprocess): same waveforms as the default staging up to the
+    rounding of the folded window x normalisation table, and inside the oracle tolerance after 50 iterations."""
+    import os
+    import subprocess
+    import sys
+    mags, angs = _case([40, 9, 100, 333])
+    np.savez(str(tmp_path / 'case.npz'), **{'m%d' % i: m for i, m in enumerate(mags)}, **{'a%d' % i: a for i, a in enumerate(angs)})
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from single_speaker_tts_b200.audio import synthesis\n"
+        "z = np.load(%r)\n"
+        "mags = [z['m%%d' %% i] for i in range(4)]; angs = [z['a%%d' %% i] for i in range(4)]\n"
+        "w = synthesis.spectrograms_to_wavs(mags, 1102, 275, 2048, 50, angles=angs)\n"
+        "np.savez(%r, *w)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / 'case.npz'),
+                                 str(tmp_path / 'out.npz')))
+    env = dict(os.environ, SSTTS_GL_STAGING='bulk')
+    subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=600)
+    got = np.load(str(tmp_path / 'out.npz'))
+    ref = synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, angles=angs)
+    for i, (m, a) in enumerate(zip(mags, angs)):
+        w = got['arr_%d' % i]
+        assert w.shape == ref[i].shape and rel_l2(w, ref[i]) < 1e-4
+    orc = ra.spectrogram_to_wav(mags[2], WIN, HOP, NFFT, 50, angles=angs[2], batched_fft=True)
+    assert rel_l2(got['arr_2'], orc) <= GL_TOL
