@@ -7,6 +7,7 @@ the CPU: without the built library or without a CUDA device the calls raise.
 import collections
 import ctypes
 import threading
+import time
 
 import numpy as np
 import torch
@@ -151,6 +152,7 @@ def _offsets(counts):
 # tools/e2e_probe.py measures the trade-off (more sub-batches: shorter exposed upload, more launches).
 _GL_CHUNK_FRAMES = 10000
 _GL_CHUNK_GROWTH = 1
+_trace = None     # tools/e2e_trace.py sets this to a list: (what, sub-batch, t0, t1) host timestamps of a call
 _aux_streams = threading.local()
 
 
@@ -161,6 +163,16 @@ def _aux_stream(dev, name):
     if (dev.index, name) not in d:
         d[(dev.index, name)] = torch.cuda.Stream(device=dev)
     return d[(dev.index, name)]
+
+
+def _uploader():
+    """Single helper thread of the calling thread (kept for the thread's lifetime, so its pinned staging
+    buffers persist): packs and uploads the sub-batches of a pipelined call two ahead of the launches."""
+    ex = getattr(_aux_streams, 'uploader', None)
+    if ex is None:
+        from concurrent.futures import ThreadPoolExecutor
+        ex = _aux_streams.uploader = ThreadPoolExecutor(max_workers=1, thread_name_prefix='sstts-upload')
+    return ex
 
 
 def _split_by_frames(frames, first, growth=1):
@@ -268,18 +280,19 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         def upload(k):
             """Pack + H2D of sub-batch k on the copy stream; returns device tensors and an event."""
             i0, i1 = ranges[k]
-            with torch.cuda.stream(copy):
+            t_up = time.perf_counter() if _trace is not None else 0.0
+            with torch.cuda.device(dev), torch.cuda.stream(copy):      # also runs on the uploader thread
                 mag_dev = _hostio.upload_rows([m.T for m in mags[i0:i1]], n_bins, torch.float32, dev,
-                                              slot='mag%d' % (k & 1))
+                                              slot='mag%d' % (k % 3))
                 ph_dev = None
                 if angles is not None:
                     ph_dev = torch.view_as_real(_hostio.upload_rows(
                         [np.asarray(a).T for a in angles[i0:i1]], n_bins, torch.complex64, dev,
-                        slot='phase%d' % (k & 1)))
+                        slot='phase%d' % (k % 3)))
                 elif uniform is not None:
                     u_dev = _hostio.upload_flat([np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
                                                  for u in uniform[i0:i1]], torch.float64, dev,
-                                                slot='uni%d' % (k & 1))
+                                                slot='uni%d' % (k % 3))
                     ph_dev = torch.empty((int(sum(frames[i0:i1])), n_bins, 2), dtype=torch.float32, device=dev)
                     o = 0
                     for t in frames[i0:i1]:
@@ -290,6 +303,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                     keep.append(u_dev)
                 ev = torch.cuda.Event()
                 ev.record(copy)
+            if _trace is not None:
+                _trace.append(('upload', k, t_up, time.perf_counter()))
             return mag_dev, ph_dev, ev
 
         flag_dev = torch.zeros(1, dtype=torch.int32, device=dev) if denormalize is not None else None
@@ -304,14 +319,31 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         # call finds exactly the blocks it needs in the allocator's per-stream caches.
         keep.append(flag_dev)
         outs = []
-        nxt = upload(0)
+        # Pipelined calls: a helper thread packs (pageable -> pinned) and uploads sub-batches k + 1 and k + 2 while
+        # this thread enqueues the launches of sub-batch k, so the host-side packing never sits between two
+        # launch sequences (it used to: pack(k + 1) ran on this thread after the launches of k).
+        if piped:
+            ex = _uploader()
+            futs = collections.deque(ex.submit(upload, k) for k in range(min(2, len(ranges))))
+        else:
+            nxt = upload(0)
         for k, (i0, i1) in enumerate(ranges):
+            t_w = time.perf_counter() if _trace is not None else 0.0
+            if piped:
+                nxt = futs.popleft().result()
+                if k + 2 < len(ranges):
+                    futs.append(ex.submit(upload, k + 2))
+            if _trace is not None:
+                _trace.append(('wait', k, t_w, time.perf_counter()))
             mag_dev, phase_dev, ev = nxt
             plan, fo = get_plan(i0, i1)
             tf = int(fo[-1])
             comp = compute[k % len(compute)]
             with torch.cuda.stream(comp):
                 comp.wait_event(ev)
+                if _trace is not None:
+                    g0 = torch.cuda.Event(enable_timing=True)
+                    g0.record(comp)
                 if denormalize is not None:
                     ref_db, max_db, power = [float(v) for v in denormalize]
                     _lib.check(lib.sstts_denormalize_magnitude(_ptr(mag_dev), tf * n_bins, ref_db, max_db, power,
@@ -333,6 +365,10 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                                                             _ptr(wav_dev), _ptr(mse_dev), _stream_ptr()))
                 if normalize_peak:
                     _lib.check(lib.sstts_peak_normalize(plan.handle, _ptr(wav_dev), _stream_ptr()))
+                if _trace is not None:
+                    g1 = torch.cuda.Event(enable_timing=True)
+                    g1.record(comp)
+                    _trace.append(('gpu', k, g0, g1))
                 # results go back on their own stream so that the next iterations start at once
                 if piped:
                     done = torch.cuda.Event()
@@ -341,8 +377,8 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
                 keep.append((mag_dev, phase_dev, ws, wav_dev, mse_dev, plan))   # the plan outlives its launches
             with torch.cuda.stream(back):
                 outs.append((_hostio.download(wav_dev), _hostio.download(mse_dev) if return_mse else None, so, fo))
-            if k + 1 < len(ranges):
-                nxt = upload(k + 1)          # host packing + H2D overlap the iterations just enqueued
+            if _trace is not None:
+                _trace.append(('enqueue', k, t_w, time.perf_counter()))
         if piped:
             compute[1].synchronize()
         flag = _hostio.download(flag_dev) if flag_dev is not None else None
