@@ -368,6 +368,33 @@ class Harness:
         return (ms, calls) if per_call else ms
 
 
+def host_pack_bandwidth(H):
+    """Aggregate rate at which all ranks together can pack pageable arrays into pinned staging buffers (the
+    host-side step of every end-to-end call with ordinary numpy inputs), measured with the ranks running
+    simultaneously: a 256 MB copy per rank on its io threads.  End-to-end numbers at N GPUs cannot exceed
+    this rate divided by the staged bytes per audio-second."""
+    from concurrent.futures import ThreadPoolExecutor
+    torch = H.torch
+    n = 64 << 20
+    src = np.ones(n, dtype=np.float32)
+    dst = torch.empty(n, dtype=torch.float32, pin_memory=True).numpy()
+    parts = H.io_threads
+    step = n // parts
+
+    def run(ex):
+        list(ex.map(lambda i: np.copyto(dst[i * step:(i + 1) * step], src[i * step:(i + 1) * step]), range(parts)))
+
+    with ThreadPoolExecutor(max_workers=parts) as ex:
+        run(ex)
+        H.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            run(ex)
+        dt = (time.perf_counter() - t0) / 3
+    dt = H.max_over_ranks(dt)
+    return H.world * n * 4 / dt / 1e9
+
+
 def bench_primary(H, args):
     """configs[2] (Griffin-Lim, the JSON line's metric) and configs[1] (features) on 256 clips per rank."""
     import ctypes
@@ -548,6 +575,7 @@ def bench_primary(H, args):
                      'ms_per_step': f_e2e_ms / e2e_steps, 'per_call_ms_rank0': f_e2e_calls,
                      'pinned_inputs_value': audio_in_total * e2e_steps / (f_e2e_pin_ms / 1000.0)}
 
+    pack_gbs = host_pack_bandwidth(H)
     roofline = {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                 'frac': gl_achieved / peak_gbs, 'traffic': measured_ncu(GL_KERNEL, 'dram_bytes_per_launch'),
                 'kernel': 'gl_step_kernel', 'peak_source': peak_src, 'ms_per_launch': iter_ms,
@@ -570,7 +598,10 @@ def bench_primary(H, args):
         'gpu_launches': args.steps * (GL_ITERS + 2),
         'roofline': roofline,
         'clocks': clocks,
-        'host': {'cores': len(os.sched_getaffinity(0)), 'io_threads_per_rank': H.io_threads},
+        'host': {'cores': len(os.sched_getaffinity(0)), 'io_threads_per_rank': H.io_threads,
+                 'pack_gbs_all_ranks': pack_gbs,
+                 'note': 'pageable-input e2e stages 4.1 KB per frame through pinned memory: at most pack_gbs_all_ranks / '
+                         '(329.5 KB per audio-second) audio-s/s on this host, whatever the number of GPUs'},
         'features': {'metric': 'feature_audio_sec_per_sec',
                      'workload': 'BASELINE configs[1]: STFT -> linear + 80-mel dB-normalised features, '
                                  '256 ragged clips per GPU',

@@ -20,7 +20,7 @@ mag = fb.spec.abs().contiguous().cpu().numpy()
 off = np.concatenate([[0], np.cumsum(fb.frames)])
 mags = [mag[off[i]:off[i + 1]].T for i in range(256)]
 audio_s = sum(HOP * (t - 1) for t in fb.frames) / 22050
-for first, growth in ((10000, 1), (6000, 1), (5000, 2), (4000, 2), (2500, 2), (2500, 3), (8000, 1.5), (3000, 1.5), (20000, 1)):
+for first, growth in ((10000, 1), (6000, 1), (5000, 2), (2500, 2), (8000, 1.5), (3000, 1.5), (14000, 1), (20000, 1)):
     _runtime._GL_CHUNK_FRAMES, _runtime._GL_CHUNK_GROWTH = first, growth
     n_sub = len(_runtime._split_by_frames(list(fb.frames), first, growth))
     for _ in range(4):
