@@ -300,6 +300,22 @@ def cpu_baselines():
     return out
 
 
+def cpu_baselines_in_subprocess(timeout_s=420):
+    """The CPU baselines fork worker pools; forking THIS process -- CUDA initialised, helper threads of the
+    staging pipeline alive -- can leave a child waiting for a lock that a thread which does not exist in the
+    child held at fork time.  They therefore run in a fresh interpreter (bench.py --cpu-baseline-only), with
+    a time limit so that the benchmark line is printed in any case."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-baseline-only'],
+                             capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+        if out.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {'error': 'cpu baseline subprocess failed (rc %d): %s' % (out.returncode, out.stderr[-300:])}
+    except subprocess.TimeoutExpired:
+        return {'error': 'cpu baseline subprocess exceeded %d s' % timeout_s}
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -740,7 +756,7 @@ def run_ours(args):
             gl4096 = bench_gl_sharded(H, args, args.clips or 4096)
             line['corpus'], line['gl4096'] = corpus, gl4096
         if H.rank == 0 and H.world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baselines()
+            line['cpu_baseline'] = cpu_baselines_in_subprocess()
         else:
             line['cpu_baseline'] = None
     elif args.workload == 'corpus':
@@ -772,7 +788,15 @@ def main():
     ap.add_argument('--corpus-chunk', type=int, default=16 << 20, help='samples per device batch of the corpus pass')
     ap.add_argument('--ref-items', type=int, default=0,
                     help='--impl reference: utterances per step (default 2 x host cores)')
+    ap.add_argument('--cpu-baseline-only', action='store_true',
+                    help='print the CPU baselines (oracle on host cores) as one JSON object and exit')
     args = ap.parse_args()
+    # a benchmark that hangs is worse than one that fails: after 15 minutes dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(900, exit=True)
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baselines()), flush=True)
+        return
     if args.impl == 'reference':
         run_reference(args)
     else:
