@@ -52,7 +52,7 @@ GL_BYTES_FINAL_PER_FRAME = 13400
 FEAT_BYTES_PER_FRAME = 4420   # (1025 + 80) float32 written per frame; + 4 bytes per input sample
 CONSTS = (35.66, 100.0, 6.02, 99.89)   # datasets/lj_speech.py:20-29 (lin ref, lin max, mel ref, mel max)
 
-GL_KERNEL = 'gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>'
+GL_KERNEL = 'gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0, 0>'
 FEAT_KERNELS = {'f64': 'stft_feature_kernel<double, StaticGeom<1102, 275, 2048>, 4, 1>',
                 'f32': 'stft_feature_kernel<float, StaticGeom<1102, 275, 2048>, 8, 1>'}
 

@@ -56,7 +56,7 @@ def first_index(pattern):
 
 # per-frame SASS phase tables: (file suffix, kernel substring, frames of that launch, title)
 for suffix, pat, frames, title in (
-        ('gl', 'gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0>', 112916, 'gl_step_kernel<float, model geometry> (iteration launch)'),
+        ('gl', 'gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0, 0>', 112916, 'gl_step_kernel<float, model geometry> (iteration launch)'),
         ('feat_f32', 'stft_feature_kernel<float, StaticGeom<1102, 275, 2048>, 8, 1>', 112916, 'stft_feature_kernel<float, model geometry, fused dB mode>'),
         ('feat_f64', 'stft_feature_kernel<double, StaticGeom<1102, 275, 2048>, 4, 1>', 112916, 'stft_feature_kernel<double, model geometry, fused dB mode>'),
         ('stats_f64', 'stft_feature_kernel<double, NativeGeom1024<1024, 256>, 4, 1>', 121282, 'stft_feature_kernel<double, native n_fft 1024, fused statistics mode>')):
