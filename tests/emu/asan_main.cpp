@@ -28,6 +28,14 @@ int main() {
     if (emu_griffin_lim(1024, 256, prec, (int)frames.size(), fo.data(), mag.data(), phase.data(), 1, wav.data(),
                         nullptr, 2, 2048)) return 1;
   }
+  // the bulk-copy staging variant of the float32 iteration kernel (cp.async.bulk emulated as memcpy: the 16-byte
+  // rounded source ranges must stay inside the workspace, the destinations inside the shared-memory carve-up)
+  setenv("SSTTS_GL_STAGING", "bulk", 1);
+  if (emu_griffin_lim(1102, 275, 0, (int)frames.size(), fo.data(), mag.data(), phase.data(), 3, wav.data(),
+                      mse.data(), 3, 2048)) return 1;
+  if (emu_griffin_lim(1024, 256, 0, (int)frames.size(), fo.data(), mag.data(), phase.data(), 2, wav.data(),
+                      nullptr, 2, 2048)) return 1;
+  unsetenv("SSTTS_GL_STAGING");
   // shorter transforms embedded in the 2048-point kernels: exactly-sized (sum T, n_fft/2 + 1) inputs
   for (int cfgi = 0; cfgi < 2; ++cfgi) {
     const int n_fft = cfgi ? 512 : 1024, win = cfgi ? 400 : 1024, hop = cfgi ? 100 : 256, nb = n_fft / 2 + 1;
@@ -66,6 +74,22 @@ int main() {
                                      x.data(), nullptr, lin.data(), mel.data(), nullptr, nullptr, 0, 0.0, 0.0, 0.0,
                                      0.0, 1.0, 2, 1)) return 1;
     }
+  }
+  // native n_fft 1024 path: fused statistics mode (extrema only, and with dB outputs), run-time geometry
+  for (int prec = 0; prec < 2; ++prec) {
+    long long rows = 0, rows2 = 0;
+    for (long long n : lens) { rows += 1 + n / 256; long long t = 1 + n / 200; rows2 += (t + 4) / 5 * 5; }
+    std::vector<float> lin((size_t)rows * 513), mel((size_t)rows * 80), lin2((size_t)rows2 * 513), mel2((size_t)rows2 * 80);
+    std::vector<float> spec2((size_t)rows2 * 513 * 2);
+    std::vector<double> mm(lens.size() * 4), raw2((size_t)rows2 * 80);
+    if (emu_stft_features(1024, 1024, 256, prec, 22050, 80, 0.0, 11025.0, (int)lens.size(), so.data(), 1, x.data(),
+                          nullptr, nullptr, nullptr, nullptr, mm.data(), 0, 0.0, 0.0, 0.0, 0.0, 1.0, 3, 1)) return 1;
+    if (emu_stft_features(1024, 1024, 256, prec, 22050, 80, 0.0, 11025.0, (int)lens.size(), so.data(), 1, x.data(),
+                          nullptr, lin.data(), mel.data(), nullptr, mm.data(), 1, 35.66, 100.0, 6.02, 99.89, 1.0, 2, 1)) return 1;
+    if (emu_stft_features(1024, 800, 200, prec, 22050, 80, 0.0, 8000.0, (int)lens.size(), so.data(), 5, x.data(),
+                          spec2.data(), lin2.data(), mel2.data(), raw2.data(), mm.data(), 1, 35.66, 100.0, 6.02, 99.89, 2.0, 3, 0)) return 1;
+    if (emu_stft_features(1024, 800, 200, prec, 22050, 80, 0.0, 8000.0, (int)lens.size(), so.data(), 5, x.data(),
+                          nullptr, lin2.data(), mel2.data(), nullptr, nullptr, 1, 35.66, 100.0, 6.02, 99.89, 1.0, 3, 1)) return 1;
   }
   std::vector<long long> cs(so.begin(), so.end() - 1), bounds(lens.size() * 2);
   emu_trim_bounds(x.data(), (int)lens.size(), cs.data(), lens.data(), 60.0, 2048, 512, bounds.data());
