@@ -25,8 +25,7 @@ for _ in range(4):
 import single_speaker_tts_b200 as pkg
 mag_pin = pkg.pinned_empty(mag.shape); mag_pin[:] = mag
 mags_pin = [mag_pin[off[i]:off[i + 1]].T for i in range(256)]
-for rep, mm in enumerate((mags, mags_pin, mags)):
-    pkg.set_io_threads((8, 8, 4)[rep])
+for rep, mm in enumerate((mags, mags_pin)):
     for _ in range(2):
         synthesis.spectrograms_to_wavs(mm, WIN, HOP, NFFT, 50, seed=1)
     _runtime._trace = []
@@ -34,7 +33,7 @@ for rep, mm in enumerate((mags, mags_pin, mags)):
     synthesis.spectrograms_to_wavs(mm, WIN, HOP, NFFT, 50, seed=1)
     t1 = time.perf_counter()
     tr, _runtime._trace = _runtime._trace, None
-    print('call %.2f ms (%s inputs, %d packing threads)' % ((t1 - t0) * 1e3, 'pinned' if rep == 1 else 'pageable', (8, 8, 4)[rep]))
+    print('call %.2f ms (%s inputs)' % ((t1 - t0) * 1e3, 'pinned' if rep == 1 else 'pageable'))
     gpu = [r for r in tr if r[0] == 'gpu']
     tr = [r for r in tr if r[0] != 'gpu']
     base = gpu[0][2]
