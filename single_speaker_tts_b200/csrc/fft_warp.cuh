@@ -245,8 +245,10 @@ SSTTS_HD void fft16_dit(T (&re)[32], T (&im)[32]) {
 constexpr int HPITCH = 17;
 constexpr int HPLANE_ELEMS = 32 * HPITCH + 16;      // 560: + 16 puts the second half on the other 16 banks
 template <typename T>
-SSTTS_D void halfwarp_fft512(T (&re)[32], T (&im)[32], T* xh, const typename cx_of<T>::type* tw, int hl) {
+SSTTS_D void halfwarp_fft512(T (&re)[32], T (&im)[32], T* plane, int half, const typename cx_of<T>::type* tw, int hl) {
   typedef typename cx_of<T>::type C;
+  // indexed from the warp's plane (not through a per-half pointer) so that every access compiles to LDS / STS
+  T* xh = plane + half * HPLANE_ELEMS;
   fft32<T, false, true>(re, im);
 #pragma unroll
   for (int k1 = 1; k1 < 32; ++k1) {

@@ -932,7 +932,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   // Interior tiles (no reflection, >= 3 samples of the clip on both sides of the span) are copied in
   // 16-byte chunks: the span starts `mis` floats past a 16-byte boundary of the packed wav buffer,
   // so sample s lands at buf[s + mis]; issue_stage returns mis (0 for the per-element path).
-  float* s_xbuf[2] = {s_x, s_x + xbuf_elems};
+  // the two sample buffers are addressed as s_x + k * xbuf_elems (NOT through an array of pointers: indexing one
+  // with a run-time value makes the compiler fall back to generic LD for every sample load)
   auto issue_stage = [&](int t, float* buf) -> int {
     const FeatTile tl = A.tiles[t];
     const long long soff = A.sample_off[tl.clip];
@@ -958,7 +959,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   };
   int cur = 0;
   int mis_cur = 0, mis_nxt = 0;
-  if ((int)blockIdx.x < A.n_tiles) mis_nxt = issue_stage(blockIdx.x, s_xbuf[0]);
+  if ((int)blockIdx.x < A.n_tiles) mis_nxt = issue_stage(blockIdx.x, s_x);
   sstts_cp_async_commit();
 
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
@@ -968,12 +969,12 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
     const long long r0 = A.row_off[tl.clip];
     const int n_rows = (int)(A.row_off[tl.clip + 1] - r0);
     const int a = tl.a, b = tl.b, FT = b - a;
-    const float* s_xc = s_xbuf[cur];
+    const float* s_xc = s_x + cur * xbuf_elems;
 
     sstts_cp_async_wait_all();    // this thread's part of the current span has landed
     __syncthreads();              // ... everyone's has, and the other buffer is no longer read
     mis_cur = mis_nxt;
-    if (tile + (int)gridDim.x < A.n_tiles) mis_nxt = issue_stage(tile + gridDim.x, s_xbuf[cur ^ 1]);
+    if (tile + (int)gridDim.x < A.n_tiles) mis_nxt = issue_stage(tile + gridDim.x, s_x + (cur ^ 1) * xbuf_elems);
     sstts_cp_async_commit();
     cur ^= 1;
     // zero rows appended by apply_reduction_padding (datasets/dataset_helper.py:383-393)
@@ -997,7 +998,6 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
       // the per-clip extrema (the statistics pass, datasets/statistics.py:54-66: the extrema of the dB values
       // are the dB values of the extrema, so only min / max of |X|^2 and of the mel sums are tracked per bin).
       const int half = lane >> 4, hl = lane & 15;
-      T* xh = plane + half * HPLANE_ELEMS;
       float* s_mag2 = reinterpret_cast<float*>(plane);          // after the transposes: |S| rows of both frames
       const int partner = (lane & 16) | ((16 - hl) & 15);
       float pmin = 3.0e38f, pmax = 0.0f, mmin = 3.0e38f, mmax = 0.0f;   // FAST: extrema of 4 |X|^2 and of 2 mel
@@ -1016,7 +1016,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
           re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * w2.x : T(0);
           im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * w2.y : T(0);
         }
-        halfwarp_fft512<T>(re, im, xh, s_tw, hl);
+        halfwarp_fft512<T>(re, im, plane, half, s_tw, hl);
         float* s_mag = s_mag2 + half * HMAG;
         float* lin_row = (FAST && A.lin_out) ? A.lin_out + row * n_bins : nullptr;
         // one bin, given 2 X[ko]; librosa stores X as complex64, everything downstream is float32
