@@ -153,6 +153,8 @@ inline bool build_feat_plan(int n_clips, const long long* clip_start, const long
     for (long long a = 0; a < T; a += tile_frames) {
       FeatTile t; t.clip = c; t.a = (int)a; t.b = (int)((a + tile_frames < T) ? a + tile_frames : T);
       t.last = (t.b == T) ? 1 : 0;
+      t.soff = clip_start[c]; t.r0 = P.row_off[c];
+      t.n_samples = (int)N; t.n_frames = (int)T; t.n_rows = (int)rows; t.reserved = 0;
       P.tiles.push_back(t);
       const int span = (t.b - t.a - 1) * hop + win;
       if (span > P.span_max) P.span_max = span;

@@ -797,7 +797,16 @@ __global__ void __launch_bounds__(NT) gl_finalize_kernel(const GLFinalArgs<T> A)
 // =============================================================================================
 // STFT feature pipeline
 // =============================================================================================
-struct FeatTile { int clip, a, b, last; };  // frames [a, b) of clip; last = tile holds frame T-1
+// frames [a, b) of clip; last = tile holds frame T-1.  Like GLTile the record is self-contained (the clip's
+// sample range and output rows ride along), so a kernel needs ONE independent 48-byte load per tile -- fetched
+// asynchronously into shared memory two rounds ahead -- instead of a tile -> clip -> offsets chain of dependent
+// global loads at every tile start (12 % of the feature kernel's stall samples in round 1).
+struct alignas(16) FeatTile {
+  int clip, a, b, last;
+  long long soff;            // first sample of the clip in the packed wav buffer
+  long long r0;              // first output row of the clip
+  int n_samples, n_frames, n_rows, reserved;
+};
 
 template <typename T> struct FeatArgs {
   const float* wav;               // packed clips
@@ -884,7 +893,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   SSTTS_DYN_SMEM(smem);
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = s_tw + 1024;
-  T* s_planes = reinterpret_cast<T*>(s_w2k + 512);
+  FeatTile* s_rec = reinterpret_cast<FeatTile*>(s_w2k + 512);      // ring of 3 tile records
+  T* s_planes = reinterpret_cast<T*>(s_rec + 3);
   constexpr int PLANE = feat_plane_elems<G>();
   T* s_win = load_window_table<T>(s_planes + W * PLANE, A.tab.window, win, lpad, tid, W * 32);
   float* s_x = reinterpret_cast<float*>(s_planes + W * PLANE + round_up4(win + WIN_TAB_PAD));
@@ -934,10 +944,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
   // so sample s lands at buf[s + mis]; issue_stage returns mis (0 for the per-element path).
   // the two sample buffers are addressed as s_x + k * xbuf_elems (NOT through an array of pointers: indexing one
   // with a run-time value makes the compiler fall back to generic LD for every sample load)
-  auto issue_stage = [&](int t, float* buf) -> int {
-    const FeatTile tl = A.tiles[t];
-    const long long soff = A.sample_off[tl.clip];
-    const int n_samples = (int)A.sample_len[tl.clip];
+  auto issue_stage = [&](const FeatTile& tl, float* buf) -> int {
+    const long long soff = tl.soff;
+    const int n_samples = tl.n_samples;
     const int span_lo = tl.a * hop + lpad;
     const int span = (tl.b - tl.a - 1) * hop + win;
     const float* x = A.wav + soff;
@@ -957,24 +966,34 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
     }
     return 0;
   };
+  // tile records travel two rounds ahead of their use: three 16-byte asynchronous copies into slot round % 3
+  auto fetch_record = [&](int t, int slot) {
+    if (tid < 3 && t < A.n_tiles)
+      sstts_cp_async16(reinterpret_cast<char*>(s_rec + slot) + 16 * tid, reinterpret_cast<const char*>(A.tiles + t) + 16 * tid);
+  };
   int cur = 0;
   int mis_cur = 0, mis_nxt = 0;
-  if ((int)blockIdx.x < A.n_tiles) mis_nxt = issue_stage(blockIdx.x, s_x);
+  const int grid = (int)gridDim.x;
+  fetch_record(blockIdx.x, 0);
+  fetch_record(blockIdx.x + grid, 1);
+  sstts_cp_async_wait_all();
+  __syncthreads();
+  if ((int)blockIdx.x < A.n_tiles) mis_nxt = issue_stage(s_rec[0], s_x);
   sstts_cp_async_commit();
 
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const FeatTile tl = A.tiles[tile];
-    const long long f0 = A.frame_off[tl.clip];
-    const int n_frames = (int)(A.frame_off[tl.clip + 1] - f0);
-    const long long r0 = A.row_off[tl.clip];
-    const int n_rows = (int)(A.row_off[tl.clip + 1] - r0);
+  int round = 0;
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += grid, ++round) {
+    sstts_cp_async_wait_all();    // this thread's part of the current span (and of the next record) has landed
+    __syncthreads();              // ... everyone's has, and the other buffer / the oldest record slot are free
+    const FeatTile tl = s_rec[round % 3];
+    const int n_frames = tl.n_frames;
+    const long long r0 = tl.r0;
+    const int n_rows = tl.n_rows;
     const int a = tl.a, b = tl.b, FT = b - a;
     const float* s_xc = s_x + cur * xbuf_elems;
-
-    sstts_cp_async_wait_all();    // this thread's part of the current span has landed
-    __syncthreads();              // ... everyone's has, and the other buffer is no longer read
     mis_cur = mis_nxt;
-    if (tile + (int)gridDim.x < A.n_tiles) mis_nxt = issue_stage(tile + gridDim.x, s_x + (cur ^ 1) * xbuf_elems);
+    fetch_record(tile + 2 * grid, (round + 2) % 3);
+    if (tile + grid < A.n_tiles) mis_nxt = issue_stage(s_rec[(round + 1) % 3], s_x + (cur ^ 1) * xbuf_elems);
     sstts_cp_async_commit();
     cur ^= 1;
     // zero rows appended by apply_reduction_padding (datasets/dataset_helper.py:383-393)
@@ -1301,7 +1320,7 @@ SSTTS_HD size_t stft_feature_smem_bytes(int warps, int win, int span_max, int n_
   const size_t mel = melp_total > 0
       ? sizeof(float) * (size_t)round_up4(2 * melp_total) + sizeof(int) * (size_t)round_up4(n_mels)
       : sizeof(T) * (size_t)round_up4(mel_nnz) + sizeof(int) * (size_t)(round_up4(n_mels + 1) + round_up4(n_mels));
-  return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) +
+  return sizeof(typename cx_of<T>::type) * (size_t)(1024 + 512) + 3 * sizeof(FeatTile) +
          sizeof(T) * (size_t)(warps * plane_elems + round_up4(win + WIN_TAB_PAD)) +
          sizeof(float) * 2 * (size_t)(round_up4(span_max) + 8) + mel;
 }
