@@ -22,11 +22,14 @@ dev = torch.device('cuda', 0)
 torch.cuda.set_device(dev)
 total_samples = sum(len(w) for w in wavs)
 print('clips', n, 'samples', total_samples, 'audio_s', total_samples / 22050)
-for rep in range(3):
+import single_speaker_tts_b200 as pkg
+IO = [int(v) for v in os.environ.get('SSTTS_PROBE_IO_THREADS', '8,8,8').split(',')]     # one pass per entry
+for rep in range(len(IO)):
+    pkg.set_io_threads(IO[rep])
     t0 = time.perf_counter()
     mean4, rows = distributed.corpus_pass(wavs, idx, n, 22050, 2048, 275, 1102, 80, 0, 8000, reduction=5)
     torch.cuda.synchronize()
-    print('corpus_pass %.1f ms  rows %d' % ((time.perf_counter() - t0) * 1000, rows))
+    print('corpus_pass %.1f ms  rows %d  io threads %d' % ((time.perf_counter() - t0) * 1000, rows, IO[rep]))
 
 # pieces
 copy = _runtime._aux_stream(dev, 'h2d')
