@@ -411,6 +411,23 @@ def host_pack_bandwidth(H):
     return H.world * n * 4 / dt / 1e9
 
 
+def host_link_bandwidth(H):
+    """Aggregate device->host and host->device rates with every rank copying at once (256 MB per rank and
+    direction between a device buffer and page-locked memory).  The feature / corpus paths return 354 KB of
+    float32 features per audio-second, so their end-to-end rate at N GPUs cannot exceed d2h / 354 KB whatever
+    N is -- on the boxes of this pool the aggregate D2H rate stops growing after two GPUs."""
+    torch = H.torch
+    n = 64 << 20
+    host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    dev = torch.empty(n, dtype=torch.float32, device=H.dev)
+    out = {}
+    for name, (dst, src) in (('d2h_gbs_all_ranks', (host, dev)), ('h2d_gbs_all_ranks', (dev, host))):
+        dst.copy_(src, non_blocking=True)
+        ms = H.timed(lambda: dst.copy_(src, non_blocking=True), 3, 1)
+        out[name] = H.world * 3 * n * 4 / (ms / 1000.0) / 1e9
+    return out
+
+
 def bench_primary(H, args):
     """configs[2] (Griffin-Lim, the JSON line's metric) and configs[1] (features) on 256 clips per rank."""
     import ctypes
@@ -592,6 +609,7 @@ def bench_primary(H, args):
                      'pinned_inputs_value': audio_in_total * e2e_steps / (f_e2e_pin_ms / 1000.0)}
 
     pack_gbs = host_pack_bandwidth(H)
+    link_gbs = host_link_bandwidth(H)
     roofline = {'bound': 'hbm', 'achieved': gl_achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                 'frac': gl_achieved / peak_gbs, 'traffic': measured_ncu(GL_KERNEL, 'dram_bytes_per_launch'),
                 'kernel': 'gl_step_kernel', 'peak_source': peak_src, 'ms_per_launch': iter_ms,
@@ -615,9 +633,10 @@ def bench_primary(H, args):
         'roofline': roofline,
         'clocks': clocks,
         'host': {'cores': len(os.sched_getaffinity(0)), 'io_threads_per_rank': H.io_threads,
-                 'pack_gbs_all_ranks': pack_gbs,
+                 'pack_gbs_all_ranks': pack_gbs, **link_gbs,
                  'note': 'pageable-input e2e stages 4.1 KB per frame through pinned memory: at most pack_gbs_all_ranks / '
-                         '(329.5 KB per audio-second) audio-s/s on this host, whatever the number of GPUs'},
+                         '(329.5 KB per audio-second) audio-s/s on this host, whatever the number of GPUs; the feature / '
+                         'corpus paths download 354 KB per audio-second: at most d2h_gbs_all_ranks / 354 KB'},
         'features': {'metric': 'feature_audio_sec_per_sec',
                      'workload': 'BASELINE configs[1]: STFT -> linear + 80-mel dB-normalised features, '
                                  '256 ragged clips per GPU',
