@@ -696,3 +696,35 @@ def test_bulk_copy_staging_variant_matches_the_default(tmp_path):
         assert w.shape == ref[i].shape and rel_l2(w, ref[i]) < 1e-4
     orc = ra.spectrogram_to_wav(mags[2], WIN, HOP, NFFT, 50, angles=angs[2], batched_fft=True)
     assert rel_l2(got['arr_2'], orc) <= GL_TOL
+
+
+def test_random_supported_geometries_vs_oracle():
+    """Run-time geometries across the supported set (the wrappers accept a subset of what librosa
+    accepts -- everything inside that subset must match the oracle): STFT / dB features for n_fft 512, 1024
+    (native transform) and 2048 with assorted window / hop lengths, Griffin-Lim for those with
+    win / 5 <= hop <= win; geometries outside raise ValueError before touching the device."""
+    rng = np.random.default_rng(123)
+    x = speech_like_clip(9000, rng)
+    cases = [(2048, 2048, 512), (2048, 1500, 375), (2048, 800, 800), (2048, 1102, 1400), (1024, 1024, 256), (1024, 800, 200),
+             (1024, 512, 512), (1024, 1000, 1023), (512, 512, 128), (512, 400, 100), (512, 256, 300)]
+    for n_fft, win, hop in cases:
+        S = features.linear_scale_spectrogram(x, n_fft, hop, win)
+        Sr = ra.linear_scale_spectrogram(x, n_fft, hop, win)
+        assert S.shape == Sr.shape, (n_fft, win, hop)
+        assert np.abs(S - Sr).max() / np.abs(Sr).max() < 2e-7, (n_fft, win, hop)
+        M = features.mel_scale_spectrogram(x, n_fft, 22050, 40, 50, 7000, hop, win, 1)
+        Mr = ra.mel_scale_spectrogram(x, n_fft, 22050, 40, 50, 7000, hop, win, 1)
+        assert np.abs(M - Mr).max() / np.abs(Mr).max() < 1e-6, (n_fft, win, hop)
+        if hop <= win and -(-win // hop) <= 5:
+            m = np.abs(Sr)
+            a = np.exp(2j * np.pi * np.random.RandomState(n_fft + win + hop).rand(*m.shape))
+            w, mse = synthesis.griffin_lim_v2(m, win, hop, n_fft, 3, angles=a)
+            ref, rmse = ra.griffin_lim_v2(m, win, hop, n_fft, 3, angles=a, batched_fft=True)
+            assert w.shape == ref.shape and rel_l2(w, ref) < 1e-5, (n_fft, win, hop)
+            assert abs(mse - rmse) / rmse < 1e-4
+        else:
+            with pytest.raises(ValueError, match='Griffin-Lim'):
+                synthesis.spectrogram_to_wav(np.abs(Sr), win, hop, n_fft, 1)
+    for bad in ((4096, 4096, 1024), (2048, 1101, 275), (1024, 1024, 2000)):
+        with pytest.raises(ValueError):
+            features.linear_scale_spectrogram(x, *bad[:1], bad[2], bad[1])
