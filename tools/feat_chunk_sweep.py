@@ -32,8 +32,9 @@ def wall(fn, n=8):
     return (time.perf_counter() - t0) / n * 1e3
 
 
-for chunk in (1 << 40, 12 << 20, 6 << 20, 4 << 20, 3 << 20, 2 << 20, 1 << 20):
-    _runtime._FEAT_CHUNK_SAMPLES = chunk
+for chunk, head in ((6 << 20, None), (6 << 20, 1 << 20), (6 << 20, 1 << 19), (6 << 20, 2 << 20), (4 << 20, 1 << 20), (3 << 20, 1 << 20),
+                    (8 << 20, 1 << 20), (6 << 20, None)):
+    _runtime._FEAT_CHUNK_SAMPLES, _runtime._FEAT_CHUNK_HEAD = chunk, head
     a = wall(lambda: features.features_batch(pclips, 2048, 275, 1102, 22050, 80, 0, 8000, *consts, reduction=5))
     b = wall(lambda: features.features_batch(clips, 2048, 275, 1102, 22050, 80, 0, 8000, *consts, reduction=5))
-    print('chunk %10d samples: pinned %.2f ms, pageable %.2f ms' % (chunk, a, b))
+    print('chunk %10d samples, first %s: pinned %.2f ms, pageable %.2f ms' % (chunk, head, a, b))
