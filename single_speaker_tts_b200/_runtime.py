@@ -153,6 +153,7 @@ def _offsets(counts):
 _GL_CHUNK_FRAMES = 10000
 _GL_CHUNK_GROWTH = 1
 _GL_CHUNK_HEAD = None
+_GL_CHUNK_CAP = None
 _trace = None     # tools/e2e_trace.py sets this to a list: (what, sub-batch, t0, t1) host timestamps of a call
 _aux_streams = threading.local()
 
@@ -176,16 +177,18 @@ def _uploader():
     return ex
 
 
-def _split_by_frames(frames, first, growth=1, head=None):
-    """Contiguous index ranges of roughly first, first * growth, first * growth ** 2, ... frames;
-    a short remainder is merged into the last range.  ``head``: size of the very first range only (a small
-    first sub-batch gets the device started while the rest is still being packed)."""
+def _split_by_frames(frames, first, growth=1, head=None, cap=None):
+    """Contiguous index ranges of roughly first, first * growth, first * growth ** 2, ... frames (at most
+    ``cap`` each); a short remainder is merged into the last range.  ``head``: size of the very first range
+    only (a small first sub-batch gets the device started while the rest is still being packed)."""
     ranges, i0, acc, limit = [], 0, 0, (head or first)
     for i, t in enumerate(frames):
         acc += t
         if acc >= limit:
             ranges.append((i0, i + 1))
             i0, acc, limit = i + 1, 0, (first if (head and len(ranges) == 1) else limit * growth)
+            if cap:
+                limit = min(limit, cap)
     if i0 < len(frames):
         if ranges and acc * 4 < limit // max(growth, 1):
             ranges[-1] = (ranges[-1][0], len(frames))
@@ -250,7 +253,7 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
         seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
     cfg = _make_config(n_fft, win_length, hop_length, precision)
     i64p = ctypes.POINTER(ctypes.c_int64)
-    ranges = _split_by_frames(frames, _GL_CHUNK_FRAMES, _GL_CHUNK_GROWTH, head=_GL_CHUNK_HEAD)
+    ranges = _split_by_frames(frames, _GL_CHUNK_FRAMES, _GL_CHUNK_GROWTH, head=_GL_CHUNK_HEAD, cap=_GL_CHUNK_CAP)
     frame_base = _offsets(frames)
 
     def get_plan(i0, i1):
