@@ -269,9 +269,23 @@ int configure_kernel(K kernel, int threads, size_t smem, int* blocks_per_sm) {
 // ----------------------------------------------------------------------------------------------
 // plans
 // ----------------------------------------------------------------------------------------------
+// CUDA graph of the iteration + finalize launches of one small call, cached per plan and buffer set.
+struct GLGraphKey {
+  const void* mag; const void* ws; const void* wav; const void* mse; int n_iter, variant;
+  bool operator==(const GLGraphKey& o) const {
+    return mag == o.mag && ws == o.ws && wav == o.wav && mse == o.mse && n_iter == o.n_iter && variant == o.variant;
+  }
+};
+struct GLGraphEntry {
+  GLGraphKey key;
+  cudaGraphExec_t exec = nullptr;
+};
+
 struct sstts_gl_plan {
   sstts_stft_config cfg;
   GLPlanHost host;
+  mutable std::mutex graph_mu;
+  mutable std::vector<GLGraphEntry> graphs;   // see run_griffin_lim
   std::shared_ptr<StaticTables> st;     // transform tables + window (shared, cached per configuration)
   DeviceBlob blob;                      // offset tables + tile records of this batch shape
   long long* d_frame_off = nullptr;
@@ -346,6 +360,8 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
 
 void sstts_gl_plan_destroy(sstts_gl_plan* P) {
   if (!P) return;
+  for (auto& g : P->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   P->blob.release();
   delete P;
 }
@@ -372,6 +388,45 @@ bool gl_bulk_requested() {
   return v;
 }
 
+// SSTTS_GL_GRAPH=0 disables the CUDA-graph path of small calls (read once per process).
+bool gl_graphs_enabled() {
+  static const bool v = [] { const char* e = getenv("SSTTS_GL_GRAPH"); return !(e && std::string(e) == "0"); }();
+  return v;
+}
+
+// The launches after the synthesis step: n_iter iteration kernels + finalize, enqueued on `st`.
+template <typename T, typename G, int W, bool BULK>
+int enqueue_iterations(const sstts_gl_plan* P, GLArgs<T> A, T* const (&buf)[4], int n_iter, float* wav_out,
+                       double* mse_frame, size_t smem, int grid_i, int grid_m, cudaStream_t st) {
+  const GLPlanHost& H = P->host;
+  const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
+  int cur = 0;
+  for (int it = 0; it < n_iter; ++it) {
+    A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
+    A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
+    if (it == n_iter - 1 && mse_frame) {
+      A.mse_frame = mse_frame;
+      gl_step_kernel<T, G, W, false, true, BULK><<<grid_m, W * 32, smem, st>>>(A);
+    } else {
+      gl_step_kernel<T, G, W, false, false, BULK><<<grid_i, W * 32, smem, st>>>(A);
+    }
+    CU(cudaGetLastError());
+    cur ^= 1;
+  }
+  GLFinalArgs<T> F;
+  F.pin0 = buf[2 * cur]; F.pin1 = buf[2 * cur + 1];
+  F.frame_off = P->d_frame_off; F.pad_off = P->d_pad_off; F.sample_off = P->d_sample_off;
+  F.tiles = P->d_tiles; F.n_tiles = A.n_tiles;
+  F.window = A.tab.window;
+  F.wav_out = wav_out;
+  F.win = H.win; F.hop = H.hop; F.n_fft = H.n_fft;
+  int grid_f = n_sms * 8;
+  if (grid_f > A.n_tiles) grid_f = A.n_tiles;
+  gl_finalize_kernel<T, G, 256><<<grid_f, 256, sizeof(T) * (round_up4(H.win) + round_up4(H.hop)), st>>>(F);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 template <typename T, typename G, int W, bool BULK>
 int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase0, uint64_t seed,
                     int64_t first, int n_iter, void* workspace, float* wav_out, double* mse_frame,
@@ -379,7 +434,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   const GLPlanHost& H = P->host;
   if (H.tiles.empty()) return 0;
   T* ws = reinterpret_cast<T*>(workspace);
-  T* buf[4] = {ws, ws + H.total_pad, ws + 2 * H.total_pad, ws + 3 * H.total_pad};
+  T* const buf[4] = {ws, ws + H.total_pad, ws + 2 * H.total_pad, ws + 3 * H.total_pad};
 
   GLArgs<T> A;
   A.mag = mag;
@@ -399,40 +454,68 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   if ((rc = configure_kernel(gl_step_kernel<T, G, W, false, false, BULK>, W * 32, smem, &occ_i))) return rc;
   if (mse_frame && (rc = configure_kernel(gl_step_kernel<T, G, W, false, true, BULK>, W * 32, smem, &occ_m))) return rc;
   const int n_sms = P->n_sms > 0 ? P->n_sms : 148;
-  int grid_s = n_sms * occ_s, grid_i = n_sms * occ_i;
+  int grid_s = n_sms * occ_s, grid_i = n_sms * occ_i, grid_m = n_sms * (occ_m > 0 ? occ_m : 1);
   if (grid_s > A.n_tiles) grid_s = A.n_tiles;
   if (grid_i > A.n_tiles) grid_i = A.n_tiles;
+  if (grid_m > A.n_tiles) grid_m = A.n_tiles;
 
-  // step 0: random phase -> wave_1 (written to buf[0], buf[1])
+  // step 0: random phase -> wave_1 (written to buf[0], buf[1]); always a plain launch (its arguments carry the
+  // per-call seed / phase pointer)
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
   gl_step_kernel<T, G, W, true, false, BULK><<<grid_s, W * 32, smem, st>>>(A);
   CU(cudaGetLastError());
-  int cur = 0;
-  for (int it = 0; it < n_iter; ++it) {
-    A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
-    A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
-    if (it == n_iter - 1 && mse_frame) {
-      A.mse_frame = mse_frame;
-      int grid_m = n_sms * occ_m;
-      if (grid_m > A.n_tiles) grid_m = A.n_tiles;
-      gl_step_kernel<T, G, W, false, true, BULK><<<grid_m, W * 32, smem, st>>>(A);
-    } else {
-      gl_step_kernel<T, G, W, false, false, BULK><<<grid_i, W * 32, smem, st>>>(A);
+
+  // Small calls (at most one wave of tiles: the single-utterance shape of tacotron/serve.py:39-86) replay the
+  // n_iter + 1 remaining launches as ONE CUDA graph per (plan, buffers): the second call with the same buffers
+  // captures it, later calls launch it -- one driver call instead of 51, which matters when six synthesis
+  // threads (tacotron/serve.py:69-72) issue their launches at the same time.  The caching allocator of the host
+  // hands a thread the same buffers call after call, so the steady state is all graph launches.
+  const bool small = gl_graphs_enabled() && n_iter >= 4 && A.n_tiles <= 2 * n_sms;
+  if (!small) return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
+  const GLGraphKey key{mag, workspace, wav_out, mse_frame, n_iter, (int)sizeof(T) * 2 + (BULK ? 1 : 0)};
+  cudaGraphExec_t exec = nullptr;
+  bool seen = false;
+  {
+    std::lock_guard<std::mutex> lock(P->graph_mu);
+    for (auto& g : P->graphs)
+      if (g.key == key) { seen = true; exec = g.exec; break; }
+    if (!seen) {
+      if (P->graphs.size() >= 16) {                       // oldest entry out
+        if (P->graphs.front().exec) cudaGraphExecDestroy(P->graphs.front().exec);
+        P->graphs.erase(P->graphs.begin());
+      }
+      GLGraphEntry e; e.key = key;
+      P->graphs.push_back(e);
     }
-    CU(cudaGetLastError());
-    cur ^= 1;
   }
-  GLFinalArgs<T> F;
-  F.pin0 = buf[2 * cur]; F.pin1 = buf[2 * cur + 1];
-  F.frame_off = P->d_frame_off; F.pad_off = P->d_pad_off; F.sample_off = P->d_sample_off;
-  F.tiles = P->d_tiles; F.n_tiles = A.n_tiles;
-  F.window = A.tab.window;
-  F.wav_out = wav_out;
-  F.win = H.win; F.hop = H.hop; F.n_fft = H.n_fft;
-  int grid_f = n_sms * 8;
-  if (grid_f > A.n_tiles) grid_f = A.n_tiles;
-  gl_finalize_kernel<T, G, 256><<<grid_f, 256, sizeof(T) * (round_up4(H.win) + round_up4(H.hop)), st>>>(F);
-  CU(cudaGetLastError());
+  if (exec) { CU(cudaGraphLaunch(exec, st)); return 0; }
+  if (!seen) return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
+  // second sighting of this buffer set: capture (thread-local mode: other threads keep making CUDA calls)
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
+  }
+  rc = enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess || !graph) return cuda_fail(ce, "cudaStreamEndCapture");
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) return cuda_fail(ie, "cudaGraphInstantiate");
+  {
+    std::lock_guard<std::mutex> lock(P->graph_mu);
+    bool stored = false;
+    for (auto& g : P->graphs)
+      if (g.key == key && !g.exec) { g.exec = exec; stored = true; break; }
+    if (!stored) {                                        // evicted meanwhile, or another thread was faster
+      CU(cudaGraphLaunch(exec, st));
+      CU(cudaStreamSynchronize(st));
+      cudaGraphExecDestroy(exec);
+      return 0;
+    }
+  }
+  CU(cudaGraphLaunch(exec, st));
   return 0;
 }
 
