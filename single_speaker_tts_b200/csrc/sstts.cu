@@ -465,12 +465,16 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   gl_step_kernel<T, G, W, true, false, BULK><<<grid_s, W * 32, smem, st>>>(A);
   CU(cudaGetLastError());
 
-  // Small calls (at most one wave of tiles: the single-utterance shape of tacotron/serve.py:39-86) replay the
-  // n_iter + 1 remaining launches as ONE CUDA graph per (plan, buffers): the second call with the same buffers
-  // captures it, later calls launch it -- one driver call instead of 51, which matters when six synthesis
-  // threads (tacotron/serve.py:69-72) issue their launches at the same time.  The caching allocator of the host
-  // hands a thread the same buffers call after call, so the steady state is all graph launches.
-  const bool small = gl_graphs_enabled() && n_iter >= 4 && A.n_tiles <= 2 * n_sms;
+  // Calls of up to kGraphTiles tiles (the single-utterance shape of tacotron/serve.py:39-86, and the ~1,250-tile
+  // sub-batches of the pipelined batch call) replay the n_iter + 1 remaining launches as ONE CUDA graph per
+  // (plan, buffers): the second call with the same buffers captures it, later calls launch it -- one driver
+  // call instead of 51, which matters when six synthesis threads (tacotron/serve.py:69-72) issue their
+  // launches at the same time (p99 18.6 -> 3.8 ms) and takes 1 ms off the 33 ms of a pipelined 256-utterance
+  // call.  The caching allocator of the host hands a thread the same buffers call after call, so the steady
+  // state is all graph launches.  Larger launches (0.5 ms per kernel) gain nothing and stay plain.
+  constexpr int kGraphTiles = 4096;
+  static const int tile_limit = [] { const char* e = getenv("SSTTS_GL_GRAPH_TILES"); return e ? atoi(e) : 0; }();
+  const bool small = gl_graphs_enabled() && n_iter >= 4 && A.n_tiles <= (tile_limit > 0 ? tile_limit : kGraphTiles);
   if (!small) return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
   const GLGraphKey key{mag, workspace, wav_out, mse_frame, n_iter, (int)sizeof(T) * 2 + (BULK ? 1 : 0)};
   cudaGraphExec_t exec = nullptr;
