@@ -517,13 +517,17 @@ def bench_primary(H, args):
 
     e2e_steps = max(1, min(args.steps, 5))
     e2e_warm = max(3, args.warmup)
-    for _ in range(2):
+    # steady state first: the sub-batch plans, the pinned staging buffers and the cached CUDA graphs of the
+    # sub-batches (captured at the fourth call with the same buffers) all exist before anything is timed
+    for _ in range(8):
         gl_e2e()
     c0 = alloc_counters()
     gl_e2e_ms, gl_e2e_calls = H.timed(gl_e2e, e2e_steps, e2e_warm, per_call=True)
     c1 = alloc_counters()
     e2e_allocs = {k: c1[k] - c0[k] for k in c1}      # cudaMalloc / cudaHostAlloc calls inside the e2e loop
     gl_e2e_value = total_audio * e2e_steps / (gl_e2e_ms / 1000.0)
+    for _ in range(6):
+        gl_e2e_pinned()
     gl_e2e_pin_ms = H.timed(gl_e2e_pinned, e2e_steps, e2e_warm)
     h2d = total_frames * N_BINS * 4
     d2h = n_samples * 4

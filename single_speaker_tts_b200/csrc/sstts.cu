@@ -279,6 +279,7 @@ struct GLGraphKey {
 struct GLGraphEntry {
   GLGraphKey key;
   cudaGraphExec_t exec = nullptr;
+  int seen = 0;               // calls with this buffer set so far
 };
 
 struct sstts_gl_plan {
@@ -467,7 +468,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
 
   // Calls of up to kGraphTiles tiles (the single-utterance shape of tacotron/serve.py:39-86, and the ~1,250-tile
   // sub-batches of the pipelined batch call) replay the n_iter + 1 remaining launches as ONE CUDA graph per
-  // (plan, buffers): the second call with the same buffers captures it, later calls launch it -- one driver
+  // (plan, buffers): a repeated call with the same buffers captures it, later calls launch it -- one driver
   // call instead of 51, which matters when six synthesis threads (tacotron/serve.py:69-72) issue their
   // launches at the same time (p99 18.6 -> 3.8 ms) and takes 1 ms off the 33 ms of a pipelined 256-utterance
   // call.  The caching allocator of the host hands a thread the same buffers call after call, so the steady
@@ -477,24 +478,28 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   const bool small = gl_graphs_enabled() && n_iter >= 4 && A.n_tiles <= (tile_limit > 0 ? tile_limit : kGraphTiles);
   if (!small) return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
   const GLGraphKey key{mag, workspace, wav_out, mse_frame, n_iter, (int)sizeof(T) * 2 + (BULK ? 1 : 0)};
+  // capture + instantiation cost about as much as five sets of plain launches: a single-wave call (the latency
+  // path) captures at its second sighting, a larger one at its fourth
+  const int capture_at = A.n_tiles <= 2 * n_sms ? 2 : 4;
   cudaGraphExec_t exec = nullptr;
   bool seen = false;
+  bool capture = false;
   {
     std::lock_guard<std::mutex> lock(P->graph_mu);
     for (auto& g : P->graphs)
-      if (g.key == key) { seen = true; exec = g.exec; break; }
+      if (g.key == key) { seen = true; exec = g.exec; capture = !exec && ++g.seen >= capture_at; break; }
     if (!seen) {
       if (P->graphs.size() >= 16) {                       // oldest entry out
         if (P->graphs.front().exec) cudaGraphExecDestroy(P->graphs.front().exec);
         P->graphs.erase(P->graphs.begin());
       }
-      GLGraphEntry e; e.key = key;
+      GLGraphEntry e; e.key = key; e.seen = 1;
       P->graphs.push_back(e);
     }
   }
   if (exec) { CU(cudaGraphLaunch(exec, st)); return 0; }
-  if (!seen) return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
-  // second sighting of this buffer set: capture (thread-local mode: other threads keep making CUDA calls)
+  if (!capture) return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
+  // capture (thread-local mode: other threads keep making CUDA calls)
   if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     (void)cudaGetLastError();
     return enqueue_iterations<T, G, W, BULK>(P, A, buf, n_iter, wav_out, mse_frame, smem, grid_i, grid_m, st);
