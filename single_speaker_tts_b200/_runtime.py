@@ -6,6 +6,7 @@ the CPU: without the built library or without a CUDA device the calls raise.
 """
 import collections
 import ctypes
+import os
 import threading
 import time
 
@@ -258,7 +259,9 @@ def griffin_lim_batch(mags, win_length, hop_length, n_fft, n_iter, angles=None, 
 
     def get_plan(i0, i1):
         fo = _offsets(frames[i0:i1])
-        key = (dev.index, n_fft, win_length, hop_length, cfg.precision, fo.tobytes())
+        # the library picks the n_fft 1024 kernel variant at plan creation (SSTTS_GL_NATIVE1024, an A/B switch)
+        key = (dev.index, n_fft, win_length, hop_length, cfg.precision, fo.tobytes(),
+               os.environ.get('SSTTS_GL_NATIVE1024') if n_fft == 1024 else None)
 
         def factory():
             h = ctypes.c_void_p()

@@ -273,6 +273,42 @@ SSTTS_D void halfwarp_fft512(T (&re)[32], T (&im)[32], T* plane, int half, const
   fft16_dit<T, false, 16>(re, im);
 }
 
+// Inverse of halfwarp_fft512 (unscaled: 512 x the inverse DFT), the same steps backwards:
+//     pass 1  two 16-point inverse FFTs over k2 (slots 0..15: k1 = hl, slots 16..31: k1 = hl + 16)
+//     16 x 32 transpose back through the half's plane (lane hl then holds n2 = hl and all 32 k1)
+//     twiddle conj W_512^(hl * k1)     same table walk as the forward transform
+//     pass 2  32-point inverse FFT over k1
+// Input : Z[k], k = hl + (s & 16) + 32 k2, in slot (s & 16) + brev4(k2) (bit-reversed inside each 16-block --
+//         the producer is unrolled code, so this is only a renaming of registers).
+// Output: z[16 * slot + hl] in natural slots.
+template <typename T>
+SSTTS_D void halfwarp_ifft512(T (&re)[32], T (&im)[32], T* plane, int half, const typename cx_of<T>::type* tw, int hl) {
+  typedef typename cx_of<T>::type C;
+  T* xh = plane + half * HPLANE_ELEMS;
+  fft16_dit<T, true, 0>(re, im);
+  fft16_dit<T, true, 16>(re, im);
+#pragma unroll
+  for (int s = 0; s < 32; ++s) xh[(hl + (s & 16)) * HPITCH + (s & 15)] = re[s];
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) re[brev5(k1)] = xh[k1 * HPITCH + hl];
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < 32; ++s) xh[(hl + (s & 16)) * HPITCH + (s & 15)] = im[s];
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) im[brev5(k1)] = xh[k1 * HPITCH + hl];
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) {
+    const C w = tw[k1 * 16 + hl];
+    const T vr = re[brev5(k1)], vi = im[brev5(k1)];
+    re[brev5(k1)] = vr * w.x + vi * w.y;
+    im[brev5(k1)] = vi * w.x - vr * w.y;
+  }
+  fft32<T, true, true>(re, im);
+}
+
 // Per-warp transpose tile: one scalar plane of 32 x 33 (pitch 33 keeps the column-wise stores
 // and the row-wise loads bank-conflict free).  Real and imaginary parts go through the same
 // plane one after the other, which halves the shared memory per warp compared with a complex

@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -63,6 +64,21 @@ struct GLPlanHost {
   std::vector<GLTile> tiles;
   long long total_frames = 0, total_pad = 0, total_samples = 0;
 };
+
+// Griffin-Lim at n_fft = 1024 runs natively (512-point complex transform per half-warp, two frames per warp,
+// tiles of 2 x warps frames) whenever the kernel's shared memory fits the device; SSTTS_GL_NATIVE1024=0 keeps
+// the older embedding in the 2048-point transform (A/B switch, also used by the tests to cover that path).
+inline bool gl_native_1024_enabled() {
+  const char* e = getenv("SSTTS_GL_NATIVE1024");
+  return !(e && e[0] == '0');
+}
+template <typename T>
+inline bool gl_native_1024(int n_fft, int win, int hop, int warps, size_t smem_limit) {
+  if (n_fft != 1024 || !gl_native_1024_enabled()) return false;
+  if (2 * min_tile_frames(win, hop) > 2 * warps) return false;
+  const int span_max = (2 * warps - 1) * hop + win;
+  return gl_step_smem_bytes<T>(warps, win, hop, span_max, false, true) <= smem_limit;
+}
 
 inline bool build_gl_plan(int n_utts, const long long* frame_off, int win, int hop, GLPlanHost& P,
                           std::string& err, int n_fft = NFFT, int tile_frames = kTileFrames) {

@@ -103,8 +103,7 @@ typedef std::tuple<int, int, int, int, int, int, double, double, int> StaticKey;
 std::mutex g_static_mu;
 std::map<StaticKey, std::shared_ptr<StaticTables> > g_static;
 
-// native1024: tables of the feature kernel's native n_fft = 1024 transform (the Griffin-Lim kernels embed
-// n_fft = 1024 in the 2048-point transform and use the ordinary tables).
+// native1024: tables of the native n_fft = 1024 transform (halfwarp_fft512) instead of the 2048-point ones.
 int get_static_tables(const sstts_stft_config* cfg, int device, bool with_mel, bool native1024,
                       std::shared_ptr<StaticTables>* out) {
   const bool f64 = cfg->precision == SSTTS_F64;
@@ -295,6 +294,7 @@ struct sstts_gl_plan {
   GLTile* d_tiles = nullptr;
   int device = 0;
   int n_sms = 0;
+  bool native1024 = false;              // n_fft 1024 transformed natively (two frames per warp, 16-frame tiles)
 };
 
 struct sstts_feat_plan {
@@ -336,15 +336,20 @@ int sstts_gl_plan_create(const sstts_stft_config* cfg, int n_utts, const int64_t
   P->cfg = *cfg;
   std::string err;
   std::vector<long long> fo(frame_off_host, frame_off_host + n_utts + 1);
+  cudaError_t e = cudaGetDevice(&P->device);
+  if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
+  const bool f64 = cfg->precision == SSTTS_F64;
+  const int warps = f64 ? kWarps : kGlWarps;
+  const size_t smem_limit = (size_t)(max_optin_smem() > 0 ? max_optin_smem() : 0);
+  P->native1024 = f64 ? gl_native_1024<double>(cfg->n_fft, cfg->win_length, cfg->hop_length, warps, smem_limit)
+                      : gl_native_1024<float>(cfg->n_fft, cfg->win_length, cfg->hop_length, warps, smem_limit);
   if (!build_gl_plan(n_utts, fo.data(), cfg->win_length, cfg->hop_length, P->host, err, cfg->n_fft,
-                     cfg->precision == SSTTS_F64 ? kWarps : kGlWarps)) {
+                     P->native1024 ? 2 * warps : warps)) {
     delete P;
     return fail(SSTTS_ERR_INVALID, err);
   }
-  cudaError_t e = cudaGetDevice(&P->device);
-  if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaGetDevice"); }
   P->n_sms = sm_count();
-  rc = get_static_tables(cfg, P->device, false, false, &P->st);
+  rc = get_static_tables(cfg, P->device, false, P->native1024, &P->st);
   if (!rc) {
     const size_t o0 = P->blob.add(P->host.frame_off), o1 = P->blob.add(P->host.pad_off);
     const size_t o2 = P->blob.add(P->host.sample_off), o3 = P->blob.add(P->host.tiles);
@@ -449,7 +454,7 @@ int run_griffin_lim(const sstts_gl_plan* P, const float* mag, const float* phase
   A.mse_frame = nullptr;
   A.win = H.win; A.hop = H.hop; A.span_max = H.span_max; A.n_fft = H.n_fft;
 
-  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.hop, H.span_max, BULK);
+  const size_t smem = gl_step_smem_bytes<T>(W, H.win, H.hop, H.span_max, BULK, G::kNative1024);
   int occ_s = 0, occ_i = 0, occ_m = 0, rc;
   if ((rc = configure_kernel(gl_step_kernel<T, G, W, true, false, BULK>, W * 32, smem, &occ_s))) return rc;
   if ((rc = configure_kernel(gl_step_kernel<T, G, W, false, false, BULK>, W * 32, smem, &occ_i))) return rc;
@@ -747,6 +752,12 @@ static int griffin_lim_dispatch(const sstts_gl_plan* P, const float* mag_dev, co
   const bool model = is_model_geometry(P->cfg.n_fft, P->host.win, P->host.hop);
 #define GL_CALL(T, G, W, B) run_griffin_lim<T, G, W, B>(P, mag_dev, phase0_dev, seed, first, n_iter, workspace_dev, \
                                                         wav_out_dev, mse_frame_dev, st)
+  if (P->native1024) {
+    const bool stats = is_stats_geometry(P->cfg.n_fft, P->host.win, P->host.hop);   // also audio/effects.py:71-86
+    if (P->cfg.precision == SSTTS_F64)
+      return stats ? GL_CALL(double, StatsGeom, kWarps, false) : GL_CALL(double, DynGeom1024, kWarps, false);
+    return stats ? GL_CALL(float, StatsGeom, kGlWarps, false) : GL_CALL(float, DynGeom1024, kGlWarps, false);
+  }
   if (P->cfg.precision == SSTTS_F64)
     return model ? GL_CALL(double, ModelGeom, kWarps, false) : GL_CALL(double, DynGeom, kWarps, false);
   if (gl_bulk_requested()) return model ? GL_CALL(float, ModelGeom, kGlWarps, true) : GL_CALL(float, DynGeom, kGlWarps, true);

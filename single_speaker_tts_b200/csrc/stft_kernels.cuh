@@ -226,6 +226,7 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
 
 constexpr int MAX_OVERLAP = 5;  // frames covering one sample: ceil(win / hop) <= 5 (host_plan.h)
 constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
+constexpr int NATIVE_MAGROW = 516;  // native n_fft 1024 path: 513 + up to 3 alignment floats per frame (16-byte multiple)
 
 // Asynchronously stage one n-float row (n = 1025, 513 or 257) into shared memory (16-byte LDGSTS for the aligned
 // body, plain loads for the <= 3 + 3 ragged elements).  Element e lands at dst[e + mis]; returns
@@ -373,6 +374,104 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)[32], c
   }
 }
 
+// The same core for the native n_fft = 1024 path: the 16 lanes of a half-warp hold the packed spectrum of one
+// frame as halfwarp_fft512 leaves it -- slot s of lane hl is Z[k], k = hl + (s & 16) + 32 (s & 15) -- and
+// N = 512, w = exp(-2 pi i k / 1024) in the identities above.  The partner Z[512 - k] of a lower-set bin
+// (slot j < 16) of lane hl >= 1 is in slot 31 - j of lane 16 - hl of the same half; lane hl == 0 holds both
+// members of its pairs (slots (j, 16 - j) and (16 + j, 31 - j)), the DC / Nyquist pair in slot 0 and the
+// self-conjugate bin 256 in slot 8.  Every lane processes 16 pairs and hands 2 Z'[512 - k] to its partner.
+// Output: 2 Z' in slot (s & 16) + brev4(s & 15), the order halfwarp_ifft512 takes.
+template <typename T, bool FROM_PHASE, bool WANT_MSE>
+SSTTS_D void gl_frame_core_native(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)[32], const float* srow,
+                                  const float2* __restrict__ prow, const typename cx_of<T>::type* s_w2k, int lane,
+                                  double& mse_acc, unsigned long long phase_seed = 0, long long phase_base = 0) {
+  typedef typename cx_of<T>::type C;
+  const int hl = lane & 15;
+  const int partner = (lane & 16) | ((16 - hl) & 15);
+  const bool h0 = hl == 0;
+  T zkr_[16], zki_[16], rr_[16], ri_[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int sa = j < 8 ? j : 8 + j;                      // lane 0's own pairs
+    const int sb = j == 0 ? 0 : (j < 8 ? 16 - j : 39 - j);
+    const int k = !h0 ? hl + 32 * j : (j < 8 ? 32 * j : 32 * j - 240);
+    const int kn = 512 - k;
+    const C w = s_w2k[k];
+    const T sk = fabs((T)srow[k]);
+    const T sn = fabs((T)srow[kn]);
+    T ykr, yki, ynr, yni;
+    if (!FROM_PHASE) {
+      const T zr = (j >= 8 && h0) ? re[sa] : re[j];
+      const T zi = (j >= 8 && h0) ? im[sa] : im[j];
+      const T pr = __shfl_sync(0xffffffffu, h0 ? re[sb] : re[31 - j], partner);
+      const T pi = __shfl_sync(0xffffffffu, h0 ? im[sb] : im[31 - j], partner);
+      const T er = zr + pr, ei = zi - pi;   // Zk + conj Zn
+      const T dr = zr - pr, di = zi + pi;   // Zk - conj Zn
+      const T wor = w.x * di + w.y * dr;    // w * (di - i dr)
+      const T woi = w.y * di - w.x * dr;
+      const T xkr = er + wor, xki = ei + woi;      // 2 X[k]
+      const T xnr = er - wor, xni = woi - ei;      // 2 X[512 - k]
+      T m2k, m2n;
+      replace_magnitude<T>(xkr, xki, sk, ykr, yki, m2k);
+      replace_magnitude<T>(xnr, xni, sn, ynr, yni, m2n);
+      if (WANT_MSE) {
+        const double ek = (double)sk - 0.5 * sqrt((double)m2k);
+        const double en = (double)sn - 0.5 * sqrt((double)m2n);
+        mse_acc += ek * ek + en * en;
+      }
+    } else {
+      float2 pk, pn;
+      if (prow) { pk = prow[k]; pn = prow[kn]; }
+      else {   // prow == nullptr: the phase is drawn here (element index = phase_base + bin)
+        pk = seeded_phasor(phase_seed, phase_base + k);
+        pn = seeded_phasor(phase_seed, phase_base + kn);
+      }
+      ykr = sk * (T)pk.x; yki = sk * (T)pk.y;
+      ynr = sn * (T)pn.x; yni = sn * (T)pn.y;
+      if (h0 && j == 0) { yki = T(0); yni = T(0); }  // ifft(...).real drops Im of DC/Nyquist
+    }
+    const T e2r = ykr + ynr, e2i = yki - yni;   // Yk + conj Yn
+    const T d2r = ykr - ynr, d2i = yki + yni;   // Yk - conj Yn
+    const T o2r = w.x * d2r + w.y * d2i;        // conj(w) * (Yk - conj Yn)
+    const T o2i = w.x * d2i - w.y * d2r;
+    zkr_[j] = e2r - o2i; zki_[j] = e2i + o2r;   // 2 Z'[k]
+    const T znr = e2r + o2i, zni = o2r - e2i;   // 2 Z'[512 - k]
+    rr_[j] = __shfl_sync(0xffffffffu, znr, partner);   // lane hl == 0 is its own partner
+    ri_[j] = __shfl_sync(0xffffffffu, zni, partner);
+  }
+  // self-conjugate bin 256 (lane hl == 0, slot 8): X = conj(Z), Z' = conj(Y)
+  T scr = T(0), sci = T(0);
+  {
+    const T s = fabs((T)srow[256]);
+    T yr, yi;
+    if (!FROM_PHASE) {
+      T m2;
+      replace_magnitude<T>(T(2) * re[8], T(-2) * im[8], s, yr, yi, m2);
+      if (WANT_MSE && h0) {
+        const double e = (double)s - 0.5 * sqrt((double)m2);
+        mse_acc += e * e;
+      }
+    } else {
+      const float2 p = prow ? prow[256] : seeded_phasor(phase_seed, phase_base + 256);
+      yr = s * (T)p.x; yi = s * (T)p.y;
+    }
+    scr = T(2) * yr; sci = T(-2) * yi;
+  }
+  // assemble the slots: lanes hl >= 1 keep 2 Z'[k] of step j in slot j and receive slot 31 - j; lane hl == 0
+  // keeps step j in slot sa(j) and its own 2 Z'[512 - k] in slot sb(j)
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    const int os = (s & 16) + brev4(s & 15);
+    T vr, vi;
+    if (s < 8) { vr = zkr_[s]; vi = zki_[s]; }
+    else if (s == 8) { vr = h0 ? scr : zkr_[8]; vi = h0 ? sci : zki_[8]; }
+    else if (s < 16) { vr = h0 ? rr_[16 - s] : zkr_[s]; vi = h0 ? ri_[16 - s] : zki_[s]; }
+    else if (s < 24) { vr = h0 ? zkr_[s - 8] : rr_[31 - s]; vi = h0 ? zki_[s - 8] : ri_[31 - s]; }
+    else { vr = h0 ? rr_[39 - s] : rr_[31 - s]; vi = h0 ? ri_[39 - s] : ri_[31 - s]; }
+    ro[os] = vr; io[os] = vi;
+  }
+}
+
 // Shared-memory carve-up of the Griffin-Lim step kernel.
 // Two staging variants of the iteration kernel (template parameter BULK of gl_step_kernel):
 //   BULK = false  every thread loads, normalises and stores its samples of the next tile after the gather
@@ -386,19 +485,32 @@ SSTTS_D void gl_frame_core(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)[32], c
 // phase, so the library runs BULK = false unless SSTTS_GL_STAGING=bulk is set (sstts.cu).
 template <typename T> struct GLSmem {
   typedef typename cx_of<T>::type C;
-  int plane_elems;   // per-warp plane: transpose tile, later the windowed output frame
+  int plane_elems;   // per-warp region: transpose tile(s), later the windowed output frame(s)
+  int frame_pitch;   // distance between the output frames of consecutive frames of the tile
   int edge_elems;    // one neighbour edge region ((win - hop) samples + alignment slack)
   size_t off_w2k, off_win, off_wr, off_rw, off_plane, off_mag, off_yin, off_edge, off_bar, total;
-  SSTTS_HD GLSmem(int warps, int win, int hop, int span_max, bool bulk) {
-    plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
+  // native: the n_fft = 1024 path with two frames per warp.  A warp's region then holds, one after the other in
+  // time, the two half-warp transpose planes (2 x HPLANE_ELEMS) next to the two staged |S| rows
+  // (2 x NATIVE_MAGROW floats), and -- once the core has consumed the rows and the inverse transform its
+  // planes -- the two windowed output frames (2 x frame_pitch), which the gather then reads.
+  SSTTS_HD GLSmem(int warps, int win, int hop, int span_max, bool bulk, bool native = false) {
+    if (native) {
+      const size_t work = sizeof(T) * 2 * HPLANE_ELEMS + sizeof(float) * 2 * NATIVE_MAGROW;
+      const int need = (int)((work + 2 * sizeof(T) - 1) / (2 * sizeof(T)));
+      frame_pitch = round_up4(win + 2) > need ? round_up4(win + 2) : round_up4(need);
+      plane_elems = 2 * frame_pitch;
+    } else {
+      plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
+      frame_pitch = plane_elems;
+    }
     edge_elems = round_up4(win - hop > 0 ? win - hop : 0) + 8;
-    size_t o = sizeof(C) * 1024;
+    size_t o = sizeof(C) * (native ? 512 : 1024);
     off_w2k = o; o += sizeof(C) * 512;
     off_win = o; o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_wr = o; if (bulk) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_rw = o; o += sizeof(T) * round_up4(hop);
     off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
-    off_mag = o; o += sizeof(float) * (size_t)warps * MAGROW;
+    off_mag = o; if (!native) o += sizeof(float) * (size_t)warps * MAGROW;
     off_yin = o; o += sizeof(T) * (round_up4(span_max) + 8);      // + slack for the 16-byte alignment shift
     off_edge = o; if (bulk) o += sizeof(T) * 2 * (size_t)edge_elems;
     off_bar = o; o += 16;                                          // mbarrier + arrival counter
@@ -409,8 +521,13 @@ template <typename T> struct GLSmem {
 #ifndef SSTTS_CORE_BREV_OUT
 #define SSTTS_CORE_BREV_OUT 1
 #endif
+#ifndef SSTTS_STAGE_PREFETCH
+#define SSTTS_STAGE_PREFETCH 1
+#endif
 // One Griffin-Lim step over all tiles.  FROM_PHASE = true is the initial synthesis from the
-// random phase (no analysis half).  W warps per CTA, one frame per warp, tiles of <= W frames.
+// random phase (no analysis half).  W warps per CTA, one frame per warp, tiles of <= W frames -- or, with a
+// native n_fft 1024 geometry (G::kNative1024), two frames per warp (a 512-point complex transform per half-warp)
+// and tiles of <= 2 W frames.
 template <typename T, typename G, int W, bool FROM_PHASE, bool WANT_MSE, bool USE_BULK = false>
 __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel(const GLArgs<T> A) {
   typedef typename cx_of<T>::type C;
@@ -422,17 +539,21 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   const int mlo = lpad & ~1;          // even base of the output-frame slot (8-byte stores)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = W * 32;
+  constexpr bool NATIVE = G::kNative1024;
+  constexpr int F = NATIVE ? 2 * W : W;          // frames per tile
+  static_assert(!(NATIVE && USE_BULK), "the bulk-copy staging variant exists for the 2048-point kernels only");
 
   SSTTS_DYN_SMEM(smem);
-  const GLSmem<T> L(W, win, hop, A.span_max, USE_BULK);
+  const GLSmem<T> L(W, win, hop, A.span_max, USE_BULK, NATIVE);
   C* s_tw = reinterpret_cast<C*>(smem);
   C* s_w2k = reinterpret_cast<C*>(smem + L.off_w2k);
   T* s_win = load_window_table<T>(reinterpret_cast<T*>(smem + L.off_win), A.tab.window, win, lpad, tid, W * 32);
   T* s_rw = reinterpret_cast<T*>(smem + L.off_rw);
   T* s_planes = reinterpret_cast<T*>(smem + L.off_plane);
-  float* s_mag = reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
   T* s_yin = reinterpret_cast<T*>(smem + L.off_yin);
   T* plane = s_planes + warp * L.plane_elems;
+  float* s_mag = NATIVE ? reinterpret_cast<float*>(plane + 2 * HPLANE_ELEMS)
+                        : reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
   constexpr bool BULK = !FROM_PHASE && USE_BULK;
   T* s_wrtab = reinterpret_cast<T*>(smem + L.off_wr);           // window x reciprocal window sum (BULK)
   T* s_wr = s_wrtab + win_shift(lpad);
@@ -440,7 +561,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   sstts_mbar_t* s_bar = reinterpret_cast<sstts_mbar_t*>(smem + L.off_bar);
   int* s_cnt = reinterpret_cast<int*>(smem + L.off_bar + 8);    // warps that have consumed s_yin this round
 
-  for (int i = tid; i < 1024; i += NT) s_tw[i] = A.tab.tw1024[i];
+  for (int i = tid; i < (NATIVE ? 512 : 1024); i += NT) s_tw[i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
   if (BULK && tid == 0) { sstts_mbar_init(s_bar, 1); *s_cnt = 0; }
   __syncthreads();
@@ -531,7 +652,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       const T* oth = pin_oth + span_lo;
       // all global loads of the thread first (independent, in flight together), then the stores;
       // residue of sample s: (span_lo - lpad + s) mod hop = s mod hop since span_lo - lpad = a hop
-      constexpr int NS = W + MAX_OVERLAP - 1;
+      constexpr int NS = F + MAX_OVERLAP - 1;
       T x[NS], e[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
@@ -595,7 +716,72 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     const int span = (FT - 1) * hop + win;
     T* pout_own = (cur.parity ? A.pout1 : A.pout0) + poff;
 
-    if (warp < FT) {
+    if constexpr (NATIVE) {
+      // two frames per warp: half-warp h transforms frame 2 warp + h of the tile (an odd tile's last half redoes
+      // its sibling's frame and stores nothing)
+      if (2 * warp < FT) {
+        const int half = lane >> 4, hl = lane & 15;
+        const bool live = 2 * warp + half < FT;
+        const int fr = live ? 2 * warp + half : 2 * warp;
+        const long long row = f0 + a + fr;
+        const float2* prow = (FROM_PHASE && A.phase0) ? A.phase0 + row * n_bins : nullptr;
+        // |S| rows of both frames: asynchronous copies by the whole warp, consumed by the core
+        stage_row_async(s_mag, A.mag + (f0 + a + 2 * warp) * n_bins, lane, n_bins);
+        if (2 * warp + 1 < FT) stage_row_async(s_mag + NATIVE_MAGROW, A.mag + (f0 + a + 2 * warp + 1) * n_bins, lane, n_bins);
+        const float* srow = s_mag + (fr - 2 * warp) * NATIVE_MAGROW +
+                            (int)((reinterpret_cast<uintptr_t>(A.mag + row * n_bins) >> 2) & 3);
+        T re[32], im[32];
+        if (!FROM_PHASE) {
+          const T* fin = s_yin + fr * hop - lpad;                // fin[m], m in [lpad, lpad + win)
+#pragma unroll
+          for (int n1 = 0; n1 < 32; ++n1) {
+            const int m = 32 * n1 + 2 * hl;
+            const int i = m - lpad;
+            C w2; w2.x = T(0); w2.y = T(0);
+            if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
+            re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
+            im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
+          }
+          if (SSTTS_STAGE_PREFETCH && next < A.n_tiles) {        // see the 2048-point branch below
+            const int nspan = (nxt.b - nxt.a - 1) * hop + win;
+            const int lines = (nspan * (int)sizeof(T) + 127) / 128 + 1;
+            const long long base = nxt.poff + nxt.a * hop + lpad;
+            for (int t = tid; t < 2 * lines; t += NT) {
+              const int line = t < lines ? t : t - lines;
+              const T* src = ((t < lines) == (nxt.parity != 0) ? A.pin1 : A.pin0) + base;
+              sstts_prefetch_l2(reinterpret_cast<const char*>(src) + 128 * line);
+            }
+          }
+          halfwarp_fft512<T>(re, im, plane, half, s_tw, hl);
+        }
+        sstts_cp_async_wait_all();
+        __syncwarp();
+        double mse_acc = 0.0;
+        T ro[32], io[32];
+        gl_frame_core_native<T, FROM_PHASE, WANT_MSE>(re, im, ro, io, srow, prow, s_w2k, lane, mse_acc, A.phase_seed,
+                                                      A.phase_first + row * n_bins);
+        if (WANT_MSE) {
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
+          if (hl == 0 && live) A.mse_frame[row] = mse_acc;
+        }
+        halfwarp_ifft512<T>(ro, io, plane, half, s_tw, hl);
+        // windowed output frames into the warp's region (transpose planes and |S| rows are dead by now)
+        T* oplane = plane + half * L.frame_pitch;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int m = 32 * n1 + 2 * hl;
+          const int i = m - lpad;
+          if (m >= mlo && m < lpad + win + 1) {
+            const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
+            C vv;
+            vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
+            *reinterpret_cast<C*>(oplane + (m - mlo)) = vv;        // m - mlo is even
+          }
+        }
+      }
+    }
+    if constexpr (!NATIVE) if (warp < FT) {
       const long long row = f0 + a + warp;
       const float* mrow = A.mag + row * n_bins;
       const float2* prow = (FROM_PHASE && A.phase0) ? A.phase0 + row * n_bins : nullptr;
@@ -624,9 +810,6 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
           re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
           im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
         }
-#ifndef SSTTS_STAGE_PREFETCH
-#define SSTTS_STAGE_PREFETCH 1
-#endif
         if (SSTTS_STAGE_PREFETCH && !BULK && next < A.n_tiles) {
           // the next tile's span of both parity buffers is pulled into L2 while this tile is transformed
           // (one 128-byte line per thread, no registers held), so the synchronous staging after the
@@ -689,7 +872,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     // is read exactly once and all indices are compile-time
     {
       const int dl = lpad - mlo;
-      const int pe = L.plane_elems;
+      const int pe = L.frame_pitch;
       T* dst = pout_own + span_lo;
       // residues beyond the first NT (hop 275 vs 256 threads: 19 of them) would keep one warp busy
       // for a whole second pass while the others wait at the barrier: they are spread over all
@@ -697,7 +880,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       const int r_cols = hop <= NT ? hop : (hop / NT) * NT;
       const int n_left = hop - r_cols;
       if (n_left > 0) {
-        constexpr int NQ = W + MAX_OVERLAP - 1;
+        constexpr int NQ = F + MAX_OVERLAP - 1;
         for (int t = tid; t < n_left * NQ; t += NT) {
           const int q = t / n_left, r = r_cols + t % n_left;
           const int s = q * hop + r;
@@ -712,11 +895,11 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         }
       }
       for (int r = tid; r < r_cols; r += NT) {
-        T acc[W + MAX_OVERLAP - 1];
+        T acc[F + MAX_OVERLAP - 1];
 #pragma unroll
-        for (int q = 0; q < W + MAX_OVERLAP - 1; ++q) acc[q] = T(0);
+        for (int q = 0; q < F + MAX_OVERLAP - 1; ++q) acc[q] = T(0);
 #pragma unroll
-        for (int f = 0; f < W; ++f) {
+        for (int f = 0; f < F; ++f) {
           if (f < FT) {
 #pragma unroll
             for (int j = 0; j < MAX_OVERLAP; ++j) {
@@ -726,7 +909,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
           }
         }
 #pragma unroll
-        for (int q = 0; q < W + MAX_OVERLAP - 1; ++q) {
+        for (int q = 0; q < F + MAX_OVERLAP - 1; ++q) {
           const int s = q * hop + r;
           if (s < span) dst[s] = acc[q];
         }
@@ -743,8 +926,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   }
 }
 
-template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int hop, int span_max, bool bulk = false) {
-  return GLSmem<T>(warps, win, hop, span_max, bulk).total;
+template <typename T> SSTTS_HD size_t gl_step_smem_bytes(int warps, int win, int hop, int span_max, bool bulk = false,
+                                                         bool native = false) {
+  return GLSmem<T>(warps, win, hop, span_max, bulk, native).total;
 }
 
 // Partial sums -> normalised, centre-trimmed float32 waveform (the reference's final istft

@@ -36,9 +36,12 @@ int main() {
   if (emu_griffin_lim(1024, 256, 0, (int)frames.size(), fo.data(), mag.data(), phase.data(), 2, wav.data(),
                       nullptr, 2, 2048)) return 1;
   unsetenv("SSTTS_GL_STAGING");
-  // shorter transforms embedded in the 2048-point kernels: exactly-sized (sum T, n_fft/2 + 1) inputs
-  for (int cfgi = 0; cfgi < 2; ++cfgi) {
-    const int n_fft = cfgi ? 512 : 1024, win = cfgi ? 400 : 1024, hop = cfgi ? 100 : 256, nb = n_fft / 2 + 1;
+  // shorter transforms: n_fft 1024 natively (two frames per warp; compile-time and run-time geometry) and, with
+  // SSTTS_GL_NATIVE1024=0, embedded in the 2048-point kernels like n_fft 512: exactly-sized (sum T, n_fft/2 + 1) inputs
+  for (int cfgi = 0; cfgi < 4; ++cfgi) {
+    if (cfgi == 3) setenv("SSTTS_GL_NATIVE1024", "0", 1);
+    const int n_fft = cfgi == 1 ? 512 : 1024, win = cfgi == 1 ? 400 : (cfgi == 2 ? 800 : 1024);
+    const int hop = cfgi == 1 ? 100 : (cfgi == 2 ? 200 : 256), nb = n_fft / 2 + 1;
     std::vector<float> mag_s((size_t)T * nb), phase_s((size_t)T * nb * 2);
     for (size_t i = 0; i < mag_s.size(); ++i) mag_s[i] = mag[i];
     for (size_t i = 0; i < phase_s.size(); ++i) phase_s[i] = phase[i];
@@ -49,6 +52,7 @@ int main() {
       if (emu_griffin_lim(win, hop, prec, (int)frames.size(), fo.data(), mag_s.data(), phase_s.data(), 2, wav_s.data(),
                           mse.data(), 3, n_fft)) return 1;
   }
+  unsetenv("SSTTS_GL_NATIVE1024");
   std::vector<long long> lens = {1, 2, 274, 275, 276, 1500, 5000, 9000, 12345, 7001};
   std::vector<long long> so(1, 0);
   for (long long n : lens) so.push_back(so.back() + n);

@@ -66,10 +66,11 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
                const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap, int n_fft) {
   GLPlanHost H;
   std::string err;
-  if (!build_gl_plan(n_utts, frame_off, win, hop, H, err, n_fft, W)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
+  constexpr bool NATIVE = G::kNative1024;
+  if (!build_gl_plan(n_utts, frame_off, win, hop, H, err, n_fft, NATIVE ? 2 * W : W)) { fprintf(stderr, "plan: %s\n", err.c_str()); return -1; }
   if (H.tiles.empty()) return 0;
   HostTables<T> tabs;
-  fill_tables<T>(win, tabs);
+  fill_tables<T>(win, tabs, NATIVE);
   std::vector<T> ws(4 * (size_t)H.total_pad, (T)NAN);  // poison: stale reads show up as NaN
   T* buf[4] = {ws.data(), ws.data() + H.total_pad, ws.data() + 2 * H.total_pad, ws.data() + 3 * H.total_pad};
   GLArgs<T> A;
@@ -81,11 +82,12 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   A.win = win; A.hop = hop; A.span_max = H.span_max; A.n_fft = n_fft;
   // SSTTS_GL_STAGING=bulk: the bulk-copy staging variant of the float32 iteration kernel (tests run both)
   const char* stg = getenv("SSTTS_GL_STAGING");
-  const bool bulk = sizeof(T) == 4 && stg && std::string(stg) == "bulk";
-  const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max, bulk);
+  const bool bulk = !NATIVE && sizeof(T) == 4 && stg && std::string(stg) == "bulk";
+  const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max, bulk, NATIVE);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
-  if (bulk) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false, true>(A); });
+  if constexpr (!NATIVE) { if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false, true>(A); }); } }
+  if (bulk) {}
   else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false>(A); });
   int cur = 0;
   for (int it = 0; it < n_iter; ++it) {
@@ -93,10 +95,12 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
     A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
     if (it == n_iter - 1 && mse_frame) {
       A.mse_frame = mse_frame;
-      if (bulk) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true, true>(A); });
+      if constexpr (!NATIVE) { if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true, true>(A); }); } }
+      if (bulk) {}
       else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true>(A); });
     } else {
-      if (bulk) emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false, true>(A); });
+      if constexpr (!NATIVE) { if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false, true>(A); }); } }
+      if (bulk) {}
       else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false>(A); });
     }
     cur ^= 1;
@@ -188,6 +192,15 @@ int emu_griffin_lim(int win, int hop, int prec, int n_utts, const long long* fra
                     const float* phase0, int n_iter, float* wav_out, double* mse_frame, int grid_cap, int n_fft) {
   const bool model = (win == 1102 && hop == 275 && n_fft == 2048);
 #define GL_ARGS win, hop, n_utts, frame_off, mag, phase0, n_iter, wav_out, mse_frame, grid_cap, n_fft
+  // same selection rule as sstts.cu (232448 bytes: opt-in shared memory per block on sm_100)
+  const bool native = prec == 1 ? gl_native_1024<double>(n_fft, win, hop, kWarps, 232448)
+                                : gl_native_1024<float>(n_fft, win, hop, kGlWarps, 232448);
+  if (native) {
+    const bool stats = win == 1024 && hop == 256;
+    if (prec == 1)
+      return stats ? emu_gl_run<double, NativeGeom1024<1024, 256>, kWarps>(GL_ARGS) : emu_gl_run<double, DynGeom1024, kWarps>(GL_ARGS);
+    return stats ? emu_gl_run<float, NativeGeom1024<1024, 256>, kGlWarps>(GL_ARGS) : emu_gl_run<float, DynGeom1024, kGlWarps>(GL_ARGS);
+  }
   if (prec == 1)
     return model ? emu_gl_run<double, StaticGeom<1102, 275, 2048>, kWarps>(GL_ARGS) : emu_gl_run<double, DynGeom, kWarps>(GL_ARGS);
   return model ? emu_gl_run<float, StaticGeom<1102, 275, 2048>, kGlWarps>(GL_ARGS) : emu_gl_run<float, DynGeom, kGlWarps>(GL_ARGS);

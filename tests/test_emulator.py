@@ -114,22 +114,52 @@ def test_griffin_lim_dynamic_geometry(emu):
     assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < 5e-7
 
 
-@pytest.mark.parametrize('n_fft,win,hop', [(1024, 1024, 256), (512, 400, 100)])
-def test_griffin_lim_shorter_transforms(emu, n_fft, win, hop):
-    """n_fft 1024 (audio/effects.py:71-86 calls spectrogram_to_wav with 1024 / 256 / 1024) and 512,
-    embedded in the 2048-point transform: every (2048 / n_fft)-th bin, first period of the inverse."""
+@pytest.mark.parametrize('n_fft,win,hop,native', [(1024, 1024, 256, '1'), (1024, 1024, 256, '0'), (1024, 800, 200, '1'),
+                                                  (512, 400, 100, '1')])
+def test_griffin_lim_shorter_transforms(emu, monkeypatch, n_fft, win, hop, native):
+    """n_fft 1024 (audio/effects.py:71-86 calls spectrogram_to_wav with 1024 / 256 / 1024): the native path
+    (512-point complex transform per half-warp, two frames per warp, 16-frame tiles; odd tiles leave the last
+    half-warp without a frame) and, with SSTTS_GL_NATIVE1024=0, the embedding in the 2048-point transform
+    (every (2048 / n_fft)-th bin, first period of the inverse) that n_fft 512 always uses."""
+    monkeypatch.setenv('SSTTS_GL_NATIVE1024', native)
     rng = np.random.default_rng(12)
-    for T in (3, 21, 40):
+    for T in (2, 3, 21, 40):
         x = speech_like_clip(hop * (T - 1) + 7, rng)
         m = np.abs(lc.stft(x, n_fft, hop, win))
         assert m.shape == (1 + n_fft // 2, T)
         a = np.exp(2j * np.pi * np.random.RandomState(T).rand(*m.shape))
-        for prec, tol in ((1, 5e-7), (0, 1e-5)):
+        for prec, tol in ((1, 1e-6), (0, 1e-5)):
             (w,), (mse,) = emu.griffin_lim([m], [a], 2, prec=prec, win=win, hop=hop, n_fft=n_fft, want_mse=True)
             ref, rmse = ra.griffin_lim_v2(m, win, hop, n_fft, 2, angles=a, batched_fft=True)
             assert w.shape == ref.shape and not np.isnan(w).any()
             assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < tol
             assert abs(mse - rmse) / rmse < 1e-5
+
+
+def test_griffin_lim_native_1024_ragged_batch_and_seeded_phase(emu, monkeypatch):
+    """The native n_fft 1024 kernels on a ragged batch (single-frame, two-frame, odd and multi-tile
+    utterances share one launch sequence) and with the phase drawn inside the synthesis launch."""
+    monkeypatch.delenv('SSTTS_GL_NATIVE1024', raising=False)
+    rng = np.random.default_rng(5)
+    frames = [1, 2, 7, 16, 17, 33]
+    mags, angs = [], []
+    for i, T in enumerate(frames):
+        x = speech_like_clip(256 * (T - 1) + 5, rng)
+        m = np.abs(lc.stft(x, 1024, 256, 1024))
+        mags.append(m)
+        angs.append(np.exp(2j * np.pi * np.random.RandomState(i).rand(*m.shape)))
+    wavs, mses = emu.griffin_lim(mags, angs, 3, prec=0, win=1024, hop=256, n_fft=1024, want_mse=True)
+    for T, m, a, w, mse in zip(frames, mags, angs, wavs, mses):
+        assert w.shape == (256 * (T - 1),)
+        if T == 1:
+            continue
+        ref, rmse = ra.griffin_lim_v2(m, 1024, 256, 1024, 3, angles=a, batched_fft=True)
+        assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < 1e-5 and abs(mse - rmse) / rmse < 1e-5
+    a = emu.griffin_lim(mags[2:], None, 3, prec=0, win=1024, hop=256, n_fft=1024, want_mse=True)
+    b = emu.griffin_lim(mags[2:], None, 3, prec=0, win=1024, hop=256, n_fft=1024, want_mse=True)
+    for w0, w1, m, mse in zip(a[0], b[0], mags[2:], a[1]):
+        assert np.array_equal(w0, w1) and np.isfinite(w0).all() and w0.std() > 0
+        assert mse < 0.5 * np.mean(m ** 2)
 
 
 @pytest.mark.parametrize('prec,tol_lin', [(1, 5e-7), (0, 2e-3)])

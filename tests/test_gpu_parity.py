@@ -529,6 +529,39 @@ def test_griffin_lim_n_fft_1024_time_stretch_geometry():
     assert rel_l2(w512, r512) < 1e-5
 
 
+@pytest.mark.parametrize('precision,tol', [('f32', 1e-5), ('f64', 1e-6)])
+def test_griffin_lim_native_1024_transform_vs_embedded_and_oracle(precision, tol, monkeypatch):
+    """n_fft 1024 Griffin-Lim runs on the native 512-point complex transform (two frames per warp, 16-frame
+    tiles); SSTTS_GL_NATIVE1024=0 keeps the embedding in the 2048-point transform.  Both must match the
+    oracle on a ragged batch with single-frame, two-frame, odd and multi-tile utterances, for the
+    statistics / time-stretch geometry (compile-time) and a run-time one (shorter window)."""
+    rng = np.random.default_rng(77)
+    for win, hop in ((1024, 256), (800, 200)):
+        frames = [1, 2, 3, 7, 16, 17, 33, 50, 121]
+        mags, angs = [], []
+        for i, T in enumerate(frames):
+            x = speech_like_clip(hop * (T - 1) + 5, rng)
+            m = np.abs(lc.stft(x, 1024, hop, win))
+            mags.append(m)
+            angs.append(np.exp(2j * np.pi * np.random.RandomState(i).rand(*m.shape)))
+        out = {}
+        for native in ('1', '0'):
+            monkeypatch.setenv('SSTTS_GL_NATIVE1024', native)
+            wavs, mses = _runtime.griffin_lim_batch(mags, win, hop, 1024, 4, angles=angs, return_mse=True,
+                                                    precision=precision)
+            out[native] = wavs
+            for T, m, a, w, mse in zip(frames, mags, angs, wavs, mses):
+                assert w.shape == (hop * (T - 1),)
+                if T == 1:
+                    continue
+                ref, rmse = ra.griffin_lim_v2(m, win, hop, 1024, 4, angles=a, batched_fft=True)
+                assert rel_l2(w, ref) < tol, (native, win, hop, T)
+                assert abs(mse - rmse) / rmse < 1e-4
+        # two different kernels: equal up to rounding, not bit for bit (float64 results round to the same float32)
+        if precision == 'f32':
+            assert any(not np.array_equal(a, b) for a, b in zip(out['1'], out['0']))
+
+
 def test_time_stretch_matches_the_reference_recipe():
     """audio/effects.py:46-86: interpolated |STFT| (the part of the phase vocoder the reference keeps)
     and the 25-iteration n_fft-1024 reconstruction, with the same numpy-seeded initial phase."""
