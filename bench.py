@@ -15,6 +15,7 @@ The same JSON line carries, under their own keys,
   * "features":   BASELINE configs[1] (the same 256 clips) -- device-resident float64 (default) and
                   float32 transforms with their rooflines, and end to end through features_batch;
   * "statistics": the n_fft 1024 / hop 256 dB-statistics kernel of datasets/statistics.py:31-34;
+  * "griffin_lim_n_fft_1024": 25 iterations at n_fft 1024 / hop 256 (audio/effects.py:71-86), device-resident;
   * "latency":    one 1000-frame utterance through spectrogram_to_wav (tacotron/serve.py:39-86),
                   p50 / p99, alone and with 6 concurrent callers (:69-72);
   * "corpus":     BASELINE configs[3] -- 13,100 LJSpeech-length clips sharded by clip over the ranks,
@@ -596,6 +597,37 @@ def bench_primary(H, args):
     lib.sstts_feat_plan_destroy(splan)
     del wav_in, mm
 
+    # ---- Griffin-Lim at n_fft 1024 / hop 256 / win 1024, 25 iterations (audio/effects.py:71-86): the native
+    # half-warp transform, device-resident through the C ABI like `value` ----
+    fb1 = _runtime.stft_features_batch(clips, 1024, 256, 1024, want_spec=True, precision='f64', keep_on_device=True)
+    mag1 = fb1.spec.abs().contiguous()
+    del fb1
+    frames1 = [1 + len(c) // 256 for c in clips]
+    foff1 = np.concatenate([[0], np.cumsum(frames1)]).astype(np.int64)
+    cfg1 = _runtime._make_config(1024, 1024, 256, 'f32')
+    plan1 = ctypes.c_void_p()
+    _lib.check(lib.sstts_gl_plan_create(ctypes.byref(cfg1), N_UTTS,
+                                        foff1.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(plan1)))
+    ws1 = torch.empty(int(lib.sstts_gl_workspace_bytes(plan1)), dtype=torch.uint8, device=dev)
+    wav1 = torch.empty(int(lib.sstts_gl_total_samples(plan1)), dtype=torch.float32, device=dev)
+
+    def gl1_step(n_iter=25):
+        _lib.check(lib.sstts_griffin_lim_seeded(plan1, ctypes.c_void_p(mag1.data_ptr()), ctypes.c_uint64(1234), 0,
+                                                n_iter, ctypes.c_void_p(ws1.data_ptr()),
+                                                ctypes.c_void_p(wav1.data_ptr()), None, stream))
+
+    g1_ms = H.timed(gl1_step, args.steps, args.warmup) / args.steps
+    g1_base = H.timed(lambda: gl1_step(0), args.steps, 1) / args.steps
+    audio1_s = sum(256 * (t - 1) for t in frames1) / SR
+    gl_1024 = {'metric': 'griffin_lim_25it_n_fft_1024_audio_sec_per_sec',
+               'value': H.sum_over_ranks(audio1_s) / (g1_ms / 1000.0), 'unit': 'audio-s/s', 'ms_per_step': g1_ms,
+               'ms_per_iteration_launch': (g1_ms - g1_base) / 25, 'frames_per_gpu': int(foff1[-1]), 'dtype': 'f32',
+               'workload': 'the 256 clips at n_fft 1024 / hop 256 / win 1024, 25 iterations (time_stretch geometry), '
+                           'device-resident; kernel: gl_step_kernel<float, NativeGeom1024<1024, 256>, ...> '
+                           '(two frames per warp)'}
+    lib.sstts_gl_plan_destroy(plan1)
+    del mag1, ws1, wav1
+
     def feat_e2e():
         feat_api.features_batch(clips, NFFT, HOP, WIN, SR, 80, 0, 8000, *CONSTS, reduction=5)
 
@@ -648,6 +680,7 @@ def bench_primary(H, args):
                      'f64': feat['f64'], 'f32_fast': feat['f32'], 'e2e': feat_e2e_line,
                      'dtype': 'f64 (default; f32_fast is the opt-in float32 transform)'},
         'statistics': statistics,
+        'griffin_lim_n_fft_1024': gl_1024,
     }
 
 

@@ -4,7 +4,9 @@
 //   * one WARP per frame: the n_fft = 2048 real transform is a 1024-point complex FFT held in
 //     the warp's registers (fft_warp.cuh), packed z[n] = x[2n] + i x[2n+1] and (un)tangled with
 //     the conjugate-pair identities below; the pair partner lives in lane (32 - l) & 31 and is
-//     exchanged with warp shuffles;
+//     exchanged with warp shuffles; n_fft = 1024 is a 512-point complex FFT on HALF a warp, two frames per
+//     warp (halfwarp_fft512 / halfwarp_ifft512; Griffin-Lim and features), n_fft = 512 is embedded in the
+//     2048-point transform;
 //   * one CTA per TILE of consecutive frames of one utterance; the tile's sample span is staged
 //     in shared memory once (reflect padding resolved while staging), so every waveform sample
 //     crosses HBM/L2 once per tile although four to five frames overlap it;
@@ -882,7 +884,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       if (n_left > 0) {
         constexpr int NQ = F + MAX_OVERLAP - 1;
         for (int t = tid; t < n_left * NQ; t += NT) {
-          const int q = t / n_left, r = r_cols + t % n_left;
+          const int nl = n_left > 0 ? n_left : 1;      // (compile-time hop = NT: the branch is dead, keep the division defined)
+          const int q = t / nl, r = r_cols + t % nl;
           const int s = q * hop + r;
           if (s < span) {
             T acc = T(0);
