@@ -55,7 +55,7 @@ template <int WIN, int HOP, int NFFT_EFF = 2048> struct StaticGeom {
   SSTTS_HD constexpr int bin_shift() const { return NFFT_EFF == 2048 ? 0 : NFFT_EFF == 1024 ? 1 : 2; }
   // packed elements z[n] (64 samples per register slot) that overlap the window; the rest are zero
   static constexpr int ZLO = ((NFFT_EFF - WIN) / 2) / 64;
-  static constexpr int ZHI = ((NFFT_EFF - WIN) / 2 + WIN - 1) / 64;
+  static constexpr int ZHI = ((NFFT_EFF - WIN) / 2 + WIN) / 64 > 31 ? 31 : ((NFFT_EFF - WIN) / 2 + WIN) / 64;   // frames may sit one sample later (SSTTS_GL_FRAME_SHIFT)
 };
 // n_fft = 1024 transformed natively by the feature kernel: a 512-point complex FFT on half a warp, two
 // frames per warp (halfwarp_fft512) -- the geometry of datasets/statistics.py:31-34 and of the STFT in
@@ -226,6 +226,16 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
   yi = xi * inv;
 }
 
+// 1: a frame of the iteration kernel whose first sample sits at an odd offset of the staged span is transformed
+// ONE SAMPLE LATER in its zero-padded n_fft buffer (position lpad + 1 instead of lpad), so that the packed pairs
+// (x[2n], x[2n+1]) are aligned 8 / 16-byte shared-memory loads instead of two conflicting scalar ones.  A circular
+// shift only multiplies the spectrum by a phase ramp: |X| is unchanged, E/|E| * |S| carries the same ramp, and the
+// inverse transform returns the frame one sample later as well, where the output store and the gather expect it.
+// (Exactly-zero bins get the phase (1, 0) in the shifted buffer; an all-zero analysis frame with |S| != 0 does
+// not occur.)  Needs lpad + 1 + win <= 2048.
+#ifndef SSTTS_GL_FRAME_SHIFT
+#define SSTTS_GL_FRAME_SHIFT 1
+#endif
 constexpr int MAX_OVERLAP = 5;  // frames covering one sample: ceil(win / hop) <= 5 (host_plan.h)
 constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
 constexpr int NATIVE_MAGROW = 516;  // native n_fft 1024 path: 513 + up to 3 alignment floats per frame (16-byte multiple)
@@ -490,7 +500,7 @@ template <typename T> struct GLSmem {
   int plane_elems;   // per-warp region: transpose tile(s), later the windowed output frame(s)
   int frame_pitch;   // distance between the output frames of consecutive frames of the tile
   int edge_elems;    // one neighbour edge region ((win - hop) samples + alignment slack)
-  size_t off_w2k, off_win, off_wr, off_rw, off_plane, off_mag, off_yin, off_edge, off_bar, total;
+  size_t off_w2k, off_win, off_win2, off_wr, off_rw, off_plane, off_mag, off_yin, off_edge, off_bar, total;
   // native: the n_fft = 1024 path with two frames per warp.  A warp's region then holds, one after the other in
   // time, the two half-warp transpose planes (2 x HPLANE_ELEMS) next to the two staged |S| rows
   // (2 x NATIVE_MAGROW floats), and -- once the core has consumed the rows and the inverse transform its
@@ -509,6 +519,7 @@ template <typename T> struct GLSmem {
     size_t o = sizeof(C) * (native ? 512 : 1024);
     off_w2k = o; o += sizeof(C) * 512;
     off_win = o; o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
+    off_win2 = o; if (SSTTS_GL_FRAME_SHIFT && !native && !bulk) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);   // other pair alignment
     off_wr = o; if (bulk) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_rw = o; o += sizeof(T) * round_up4(hop);
     off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
@@ -557,6 +568,12 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   float* s_mag = NATIVE ? reinterpret_cast<float*>(plane + 2 * HPLANE_ELEMS)
                         : reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
   constexpr bool BULK = !FROM_PHASE && USE_BULK;
+  // frames at odd offsets of the span are transformed one sample later (see SSTTS_GL_FRAME_SHIFT)
+  constexpr bool SHIFT = (SSTTS_GL_FRAME_SHIFT != 0) && !FROM_PHASE && !USE_BULK && !NATIVE;
+  const bool shift_ok = SHIFT && lpad + 1 + win <= NFFT;
+  auto frame_shift = [&](int f) -> int { return (SHIFT && shift_ok) ? ((f * hop - lpad) & 1) : 0; };
+  T* s_win2 = s_win;   // window table with the other pair alignment (for lpad + 1)
+  if constexpr (SHIFT) s_win2 = load_window_table<T>(reinterpret_cast<T*>(smem + L.off_win2), A.tab.window, win, lpad + 1, tid, W * 32);
   T* s_wrtab = reinterpret_cast<T*>(smem + L.off_wr);           // window x reciprocal window sum (BULK)
   T* s_wr = s_wrtab + win_shift(lpad);
   T* s_edge = reinterpret_cast<T*>(smem + L.off_edge);          // raw neighbour sums of the two edge regions
@@ -789,6 +806,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       const float2* prow = (FROM_PHASE && A.phase0) ? A.phase0 + row * n_bins : nullptr;
       const float* srow = mrow;
       T re[32], im[32];
+      const int sh = frame_shift(warp);
+      const int lp = lpad + sh;                                   // position of the frame in its n_fft buffer
       if (FROM_PHASE) {
         // the frame's |S| row goes through shared memory here too: one asynchronous copy and one wait
         // instead of 33 dependent global loads inside the pair loop
@@ -800,17 +819,37 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         const int mis = stage_row_async(s_mag, mrow, lane, n_bins);
         srow = s_mag + mis;
         // bulk-staged tiles hold raw sums shifted by the alignment offset; their normalisation is in s_wr
-        const T* fin = s_yin + (cur_bulk ? ((a * hop + lpad) & 3) : 0) + warp * hop - lpad;  // fin[m], m in [lpad, lpad + win)
-        const T* wtab = cur_bulk ? s_wr : s_win;
+        const T* fin = s_yin + (cur_bulk ? ((a * hop + lpad) & 3) : 0) + warp * hop - lp;  // fin[m], m in [lp, lp + win)
+        const T* wtab = cur_bulk ? s_wr : (sh ? s_win2 : s_win);
+        // with the shift available every frame starts at an even offset of the 16-byte aligned span: (x[m], x[m+1])
+        // is one aligned load like the window pair
+        const bool paired = SHIFT && shift_ok;
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
           const int m = 64 * n1 + 2 * lane;
-          const int i = m - lpad;
-          // window pair (zero outside the window) in one aligned load; DIT pass: bit-reversed slots
-          C w2; w2.x = T(0); w2.y = T(0);
-          if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(wtab + i);
-          re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
-          im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
+          const int i = m - lp;
+          // window pair (zero outside the window) in one aligned load; DIT pass: bit-reversed slots.
+          // Slots entirely inside / outside the window for every lane and both frame positions need no guards
+          // (compile-time for the model geometry).
+          const int i_min = 64 * n1 - lpad - 1, i_max = 64 * n1 + 62 - lpad;
+          if (i_max + 1 < 0 || i_min >= win) {
+            re[brev5(n1)] = T(0); im[brev5(n1)] = T(0);
+          } else if (paired && i_min >= 0 && i_max + 1 < win) {
+            const C w2 = *reinterpret_cast<const C*>(wtab + i);
+            const C x2 = *reinterpret_cast<const C*>(fin + m);
+            re[brev5(n1)] = x2.x * w2.x;
+            im[brev5(n1)] = x2.y * w2.y;
+          } else {
+            C w2; w2.x = T(0); w2.y = T(0);
+            C x2; x2.x = T(0); x2.y = T(0);
+            if (i + 1 >= 0 && i < win) {
+              w2 = *reinterpret_cast<const C*>(wtab + i);
+              if (paired) x2 = *reinterpret_cast<const C*>(fin + m);
+              else { x2.x = i >= 0 ? fin[m] : T(0); x2.y = i + 1 < win ? fin[m + 1] : T(0); }
+            }
+            re[brev5(n1)] = (i >= 0 && i < win) ? x2.x * w2.x : T(0);
+            im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? x2.y * w2.y : T(0);
+          }
         }
         if (SSTTS_STAGE_PREFETCH && !BULK && next < A.n_tiles) {
           // the next tile's span of both parity buffers is pulled into L2 while this tile is transformed
@@ -853,17 +892,20 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
       warp_fft1024<T, true, SSTTS_CORE_BREV_OUT != 0, true>(ro, io, plane, s_tw, lane);
       // windowed output frame into the (now dead) plane; slot index = m - mlo, zero outside
       // the window so that the pair store needs no per-element guard
+      const T* wout = sh ? s_win2 : s_win;
+      const int mlo_w = lp & ~1;
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) {
         const int m = 64 * n1 + 2 * lane;
-        const int i = m - lpad;
-        if (m >= mlo && m < lpad + win + 1) {
-          const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
-          const T v0 = ro[n1] * w2.x;
-          const T v1 = io[n1] * w2.y;
-          typename cx_of<T>::type vv;
-          vv.x = v0; vv.y = v1;
-          *reinterpret_cast<typename cx_of<T>::type*>(plane + (m - mlo)) = vv;   // m - mlo is even
+        const int i = m - lp;
+        // slots inside the window for every lane and both frame positions store unconditionally
+        const bool inside = 64 * n1 >= mlo + 2 && 64 * n1 + 62 < lpad + win + 1;
+        const bool outside = 64 * n1 + 62 < mlo || 64 * n1 >= lpad + win + 2;
+        if (!outside && (inside || (m >= mlo_w && m < lp + win + 1))) {
+          const C w2 = *reinterpret_cast<const C*>(wout + i);    // zeros outside the window
+          C vv;
+          vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
+          *reinterpret_cast<C*>(plane + (m - mlo_w)) = vv;       // m - mlo_w is even
         }
       }
     }
@@ -873,8 +915,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
     // column form: a thread owns the samples s = q * hop + r of one residue r; every slot element
     // is read exactly once and all indices are compile-time
     {
-      const int dl = lpad - mlo;
       const int pe = L.frame_pitch;
+      // first sample of frame f inside its output slot: (lpad + shift) & 1
+      auto slot_off = [&](int f) -> int { return (lpad + frame_shift(f)) & 1; };
       T* dst = pout_own + span_lo;
       // residues beyond the first NT (hop 275 vs 256 threads: 19 of them) would keep one warp busy
       // for a whole second pass while the others wait at the barrier: they are spread over all
@@ -891,7 +934,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
             T acc = T(0);
             for (int j = MAX_OVERLAP - 1; j >= 0; --j) {      // ascending frame order f = q - j
               const int f = q - j, off = r + j * hop;
-              if (f >= 0 && f < FT && off < win) acc += s_planes[f * pe + off + dl];
+              if (f >= 0 && f < FT && off < win) acc += s_planes[f * pe + off + slot_off(f)];
             }
             dst[s] = acc;
           }
@@ -904,6 +947,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           if (f < FT) {
+            const int dl = slot_off(f);
 #pragma unroll
             for (int j = 0; j < MAX_OVERLAP; ++j) {
               const int off = r + j * hop;
