@@ -362,4 +362,39 @@ SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], T* xp, const typename cx_of<
   }
 }
 
+// The same transform with a COMPLEX transpose plane (32 x 33 values of 8 / 16 bytes): real and imaginary parts
+// travel together, so the exchange is 32 + 32 shared-memory instructions instead of 64 + 64 at the same number
+// of wavefronts (column-wise stores are contiguous; row-wise 8-byte loads at pitch 33 are conflict-free per
+// half-warp).  `mid()` runs between the exchange and the second pass -- the Griffin-Lim kernel issues the
+// asynchronous copy of the frame's |S| row there, into memory the plane overlaps.
+template <typename T, bool INV, bool P1_DIT, bool P2_DIT, int ZLO, int ZHI, typename Mid>
+SSTTS_D void warp_fft1024_cx(T (&re)[32], T (&im)[32], typename cx_of<T>::type* xc,
+                             const typename cx_of<T>::type* tw, int lane, Mid mid) {
+  typedef typename cx_of<T>::type C;
+  fft32<T, INV, P1_DIT, (P1_DIT ? ZLO : 0), (P1_DIT ? ZHI : 31)>(re, im);
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) {
+    const int p = P1_DIT ? k1 : brev5(k1);
+    const C w = tw[k1 * 32 + lane];
+    const T vr = re[p], vi = im[p];
+    if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
+    else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
+  }
+  __syncwarp();   // the plane may overlap data other lanes were still reading (the |S| row in the core)
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    C v; v.x = re[P1_DIT ? k1 : brev5(k1)]; v.y = im[P1_DIT ? k1 : brev5(k1)];
+    xc[k1 * XPITCH + lane] = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) {
+    const C v = xc[lane * XPITCH + n2];
+    re[P2_DIT ? brev5(n2) : n2] = v.x; im[P2_DIT ? brev5(n2) : n2] = v.y;
+  }
+  __syncwarp();
+  mid();
+  fft32<T, INV, P2_DIT>(re, im);
+}
+
 }  // namespace sstts

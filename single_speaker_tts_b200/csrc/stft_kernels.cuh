@@ -236,6 +236,11 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
 #ifndef SSTTS_GL_FRAME_SHIFT
 #define SSTTS_GL_FRAME_SHIFT 1
 #endif
+// 1: the float32 n_fft 2048 Griffin-Lim kernels exchange (re, im) pairs through a complex transpose plane
+// (warp_fft1024_cx) that overlaps the warp's |S| row buffer.
+#ifndef SSTTS_GL_COMPLEX_PLANE
+#define SSTTS_GL_COMPLEX_PLANE 1
+#endif
 constexpr int MAX_OVERLAP = 5;  // frames covering one sample: ceil(win / hop) <= 5 (host_plan.h)
 constexpr int MAGROW = 1032;  // per-warp staging of one |S| row: 1025 + up to 3 alignment floats
 constexpr int NATIVE_MAGROW = 516;  // native n_fft 1024 path: 513 + up to 3 alignment floats per frame (16-byte multiple)
@@ -500,6 +505,7 @@ template <typename T> struct GLSmem {
   int plane_elems;   // per-warp region: transpose tile(s), later the windowed output frame(s)
   int frame_pitch;   // distance between the output frames of consecutive frames of the tile
   int edge_elems;    // one neighbour edge region ((win - hop) samples + alignment slack)
+  int mag_in_plane = 0;   // > 0: offset (elements) of the warp's |S| row inside its region (complex-plane layout)
   size_t off_w2k, off_win, off_win2, off_wr, off_rw, off_plane, off_mag, off_yin, off_edge, off_bar, total;
   // native: the n_fft = 1024 path with two frames per warp.  A warp's region then holds, one after the other in
   // time, the two half-warp transpose planes (2 x HPLANE_ELEMS) next to the two staged |S| rows
@@ -513,6 +519,14 @@ template <typename T> struct GLSmem {
       plane_elems = 2 * frame_pitch;
     } else {
       plane_elems = round_up4(win + 2) > XPLANE_ELEMS ? round_up4(win + 2) : round_up4(XPLANE_ELEMS);
+      mag_in_plane = 0;
+      if (SSTTS_GL_COMPLEX_PLANE && sizeof(T) == 4) {
+        // float32: the |S| row is staged right behind the frame part of the warp's region, and the COMPLEX
+        // transpose plane (2 x XPLANE_ELEMS floats) spans both -- the row is copied in after the forward
+        // transform's exchange and is dead before the inverse transform's
+        mag_in_plane = plane_elems;
+        plane_elems += round_up4(XPLANE_ELEMS);
+      }
       frame_pitch = plane_elems;
     }
     edge_elems = round_up4(win - hop > 0 ? win - hop : 0) + 8;
@@ -523,7 +537,7 @@ template <typename T> struct GLSmem {
     off_wr = o; if (bulk) o += sizeof(T) * round_up4(win + WIN_TAB_PAD);
     off_rw = o; o += sizeof(T) * round_up4(hop);
     off_plane = o; o += sizeof(T) * (size_t)warps * plane_elems;
-    off_mag = o; if (!native) o += sizeof(float) * (size_t)warps * MAGROW;
+    off_mag = o; if (!native && !mag_in_plane) o += sizeof(float) * (size_t)warps * MAGROW;
     off_yin = o; o += sizeof(T) * (round_up4(span_max) + 8);      // + slack for the 16-byte alignment shift
     off_edge = o; if (bulk) o += sizeof(T) * 2 * (size_t)edge_elems;
     off_bar = o; o += 16;                                          // mbarrier + arrival counter
@@ -565,7 +579,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   T* s_planes = reinterpret_cast<T*>(smem + L.off_plane);
   T* s_yin = reinterpret_cast<T*>(smem + L.off_yin);
   T* plane = s_planes + warp * L.plane_elems;
+  constexpr bool CXP = (SSTTS_GL_COMPLEX_PLANE != 0) && sizeof(T) == 4 && !NATIVE;
   float* s_mag = NATIVE ? reinterpret_cast<float*>(plane + 2 * HPLANE_ELEMS)
+                 : CXP  ? reinterpret_cast<float*>(plane + L.mag_in_plane)
                         : reinterpret_cast<float*>(smem + L.off_mag) + warp * MAGROW;
   constexpr bool BULK = !FROM_PHASE && USE_BULK;
   // frames at odd offsets of the span are transformed one sample later (see SSTTS_GL_FRAME_SHIFT)
@@ -816,8 +832,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         __syncwarp();
         srow = s_mag + mis;
       } else {
-        const int mis = stage_row_async(s_mag, mrow, lane, n_bins);
-        srow = s_mag + mis;
+        srow = s_mag + (int)((reinterpret_cast<uintptr_t>(mrow) >> 2) & 3);
+        if (!CXP) stage_row_async(s_mag, mrow, lane, n_bins);
+        else sstts_prefetch_l2(reinterpret_cast<const char*>(mrow) + 128 * lane);   // copied after the exchange
         // bulk-staged tiles hold raw sums shifted by the alignment offset; their normalisation is in s_wr
         const T* fin = s_yin + (cur_bulk ? ((a * hop + lpad) & 3) : 0) + warp * hop - lp;  // fin[m], m in [lp, lp + win)
         const T* wtab = cur_bulk ? s_wr : (sh ? s_win2 : s_win);
@@ -866,7 +883,11 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
             sstts_prefetch_l2(reinterpret_cast<const char*>(src) + 128 * line);
           }
         }
-        warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
+        if constexpr (CXP)
+          warp_fft1024_cx<T, false, true, true, G::ZLO, G::ZHI>(re, im, reinterpret_cast<C*>(plane), s_tw, lane,
+                                                                  [&]() { stage_row_async(s_mag, mrow, lane, n_bins); });
+        else
+          warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
         if (BULK) {
           // this warp's samples have been consumed by the transform: the last of the tile's warps to get
           // here hands s_yin back to the copy engine for the NEXT tile, whose span then arrives while the
@@ -889,7 +910,10 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         if (lane == 0) A.mse_frame[row] = mse_acc;
       }
       // inverse transform: with the core's output in bit-reversed slots both passes are FMA-fused DIT
-      warp_fft1024<T, true, SSTTS_CORE_BREV_OUT != 0, true>(ro, io, plane, s_tw, lane);
+      if constexpr (CXP)
+        warp_fft1024_cx<T, true, SSTTS_CORE_BREV_OUT != 0, true, 0, 31>(ro, io, reinterpret_cast<C*>(plane), s_tw, lane, []() {});
+      else
+        warp_fft1024<T, true, SSTTS_CORE_BREV_OUT != 0, true>(ro, io, plane, s_tw, lane);
       // windowed output frame into the (now dead) plane; slot index = m - mlo, zero outside
       // the window so that the pair store needs no per-element guard
       const T* wout = sh ? s_win2 : s_win;
