@@ -625,6 +625,14 @@ def bench_primary(H, args):
                'workload': 'the 256 clips at n_fft 1024 / hop 256 / win 1024, 25 iterations (time_stretch geometry), '
                            'device-resident; kernel: gl_step_kernel<float, NativeGeom1024<1024, 256>, ...> '
                            '(two frames per warp)'}
+    # same byte model as the headline kernel: spectrum out and back (513 x 8 B x 2), |S| row, waveform in / out
+    g1_alg = (513 * 8 * 2 + 513 * 4 + 256 * 4 * 2) * int(foff1[-1])
+    g1_iter_ms = max(1e-9, (g1_ms - g1_base) / 25)
+    g1_kernel = 'gl_step_kernel<float, NativeGeom1024<1024, 256>, 8, 0, 0, 0>'
+    gl_1024['roofline'] = dict({'bound': 'hbm', 'achieved': g1_alg / (g1_iter_ms / 1000.0) / 1e9, 'peak': peak_gbs,
+                                'unit': 'GB/s', 'frac': g1_alg / (g1_iter_ms / 1000.0) / 1e9 / peak_gbs,
+                                'traffic': measured_ncu(g1_kernel, 'dram_bytes_per_launch'), 'kernel': g1_kernel,
+                                'algorithmic_bytes_per_launch': g1_alg, 'ms_per_launch': g1_iter_ms}, **ncu_block(g1_kernel))
     lib.sstts_gl_plan_destroy(plan1)
     del mag1, ws1, wav1
 

@@ -47,4 +47,14 @@ for prec in ('f64', 'f32'):
                                          want_minmax=True, precision=prec, keep_on_device=True)
         e1.record(); torch.cuda.synchronize()
         print('statistics', prec, 'ms', e0.elapsed_time(e1))
+# Griffin-Lim at n_fft 1024 / hop 256 (native half-warp transform)
+fb1 = _runtime.stft_features_batch(clips, 1024, 256, 1024, want_spec=True, precision='f32', keep_on_device=True)
+mag1 = fb1.spec.abs().contiguous().cpu().numpy()
+off1 = np.concatenate([[0], np.cumsum(fb1.frames)])
+mags1 = [mag1[off1[i]:off1[i + 1]].T for i in range(n_utts)]
+for rep in range(REPS):
+    e0.record()
+    _runtime.griffin_lim_batch(mags1, 1024, 256, 1024, n_iter, seed=3)
+    e1.record(); torch.cuda.synchronize()
+    print('gl n_fft 1024 n_iter', n_iter, 'ms', e0.elapsed_time(e1))
 print('ok')
