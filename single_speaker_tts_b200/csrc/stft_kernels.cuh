@@ -489,6 +489,30 @@ SSTTS_D void gl_frame_core_native(T (&re)[32], T (&im)[32], T (&ro)[32], T (&io)
   }
 }
 
+// Windowed, packed frame into the registers of a DIT first pass (bit-reversed slots): element n1 of lane l is
+// z = (x[m] w[m - lpad], x[m + 1] w[m + 1 - lpad]), m = STRIDE n1 + 2 l (STRIDE 64: one frame per warp, 32: one per
+// half-warp), zero outside the window.  PAIRED: fin + m is aligned for a two-sample load (the caller checked that
+// the frame starts at an even element of the 8-byte aligned buffer), else two scalar loads.
+template <typename T, typename S, int STRIDE, bool PAIRED>
+SSTTS_D void load_windowed_frame(T (&re)[32], T (&im)[32], const S* fin, const T* s_win, int lpad, int win, int l) {
+  typedef typename cx_of<T>::type C;
+  typedef typename cx_of<S>::type S2;
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) {
+    const int m = STRIDE * n1 + 2 * l;
+    const int i = m - lpad;
+    C w2; w2.x = T(0); w2.y = T(0);
+    S xa = S(0), xb = S(0);
+    if (i + 1 >= 0 && i < win) {
+      w2 = *reinterpret_cast<const C*>(s_win + i);       // window pair (zero outside the window) in one aligned load
+      if (PAIRED) { const S2 v = *reinterpret_cast<const S2*>(fin + m); xa = v.x; xb = v.y; }
+      else { if (i >= 0) xa = fin[m]; if (i + 1 < win) xb = fin[m + 1]; }
+    }
+    re[brev5(n1)] = (i >= 0 && i < win) ? (T)xa * w2.x : T(0);
+    im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)xb * w2.y : T(0);
+  }
+}
+
 // Shared-memory carve-up of the Griffin-Lim step kernel.
 // Two staging variants of the iteration kernel (template parameter BULK of gl_step_kernel):
 //   BULK = false  every thread loads, normalises and stores its samples of the next tile after the gather
@@ -768,15 +792,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         T re[32], im[32];
         if (!FROM_PHASE) {
           const T* fin = s_yin + fr * hop - lpad;                // fin[m], m in [lpad, lpad + win)
-#pragma unroll
-          for (int n1 = 0; n1 < 32; ++n1) {
-            const int m = 32 * n1 + 2 * hl;
-            const int i = m - lpad;
-            C w2; w2.x = T(0); w2.y = T(0);
-            if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
-            re[brev5(n1)] = (i >= 0 && i < win) ? fin[m] * w2.x : T(0);
-            im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? fin[m + 1] * w2.y : T(0);
-          }
+          // frames at even offsets of the span (all of them at hop 256 / win 1024) load their sample pairs aligned
+          if (((fr * hop - lpad) & 1) == 0) load_windowed_frame<T, T, 32, true>(re, im, fin, s_win, lpad, win, hl);
+          else load_windowed_frame<T, T, 32, false>(re, im, fin, s_win, lpad, win, hl);
           if (SSTTS_STAGE_PREFETCH && next < A.n_tiles) {        // see the 2048-point branch below
             const int nspan = (nxt.b - nxt.a - 1) * hop + win;
             const int lines = (nspan * (int)sizeof(T) + 127) / 128 + 1;
@@ -1281,15 +1299,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
         const long long row = r0 + a + jr;
         T re[32], im[32];
         const float* fin = s_xc + mis_cur + jr * hop - lpad;
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const int m = 32 * n1 + 2 * hl;
-          const int i = m - lpad;
-          C w2; w2.x = T(0); w2.y = T(0);
-          if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
-          re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * w2.x : T(0);
-          im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * w2.y : T(0);
-        }
+        // (8-byte sample-pair loads for frames at even offsets were measured here: 2-4 % SLOWER in both precisions,
+        // profiles/experiments/r2_ab_paired_loads.txt -- scalar loads)
+        load_windowed_frame<T, float, 32, false>(re, im, fin, s_win, lpad, win, hl);
         halfwarp_fft512<T>(re, im, plane, half, s_tw, hl);
         float* s_mag = s_mag2 + half * HMAG;
         float* lin_row = (FAST && A.lin_out) ? A.lin_out + row * n_bins : nullptr;
@@ -1406,15 +1418,10 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
       const long long row = r0 + a + jr;
       T re[32], im[32];
       const float* fin = s_xc + mis_cur + jr * hop - lpad;
-#pragma unroll
-      for (int n1 = 0; n1 < 32; ++n1) {
-        const int m = 64 * n1 + 2 * lane;
-        const int i = m - lpad;
-        C w2; w2.x = T(0); w2.y = T(0);
-        if (i + 1 >= 0 && i < win) w2 = *reinterpret_cast<const C*>(s_win + i);
-        re[brev5(n1)] = (i >= 0 && i < win) ? (T)fin[m] * w2.x : T(0);      // DIT pass: bit-reversed slots
-        im[brev5(n1)] = (i + 1 >= 0 && i + 1 < win) ? (T)fin[m + 1] * w2.y : T(0);
-      }
+      // float32: frames that start at an even element of the staged span load their sample pairs with one 8-byte
+      // load (fused mode 0.409 -> 0.397 ms); the float64 instances got 1-3 % slower with it and keep scalar loads
+      if (sizeof(T) == 4 && ((mis_cur + jr * hop - lpad) & 1) == 0) load_windowed_frame<T, float, 64, true>(re, im, fin, s_win, lpad, win, lane);
+      else load_windowed_frame<T, float, 64, false>(re, im, fin, s_win, lpad, win, lane);
       warp_fft1024<T, false, true, true, G::ZLO, G::ZHI>(re, im, plane, s_tw, lane);
       float* s_mag = reinterpret_cast<float*>(plane);  // transpose plane is dead: |S| of this frame
       float* lin_row = FAST ? A.lin_out + row * NBINS : nullptr;
