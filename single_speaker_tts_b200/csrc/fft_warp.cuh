@@ -367,18 +367,30 @@ SSTTS_D void warp_fft1024(T (&re)[32], T (&im)[32], T* xp, const typename cx_of<
 // of wavefronts (column-wise stores are contiguous; row-wise 8-byte loads at pitch 33 are conflict-free per
 // half-warp).  `mid()` runs between the exchange and the second pass -- the Griffin-Lim kernel issues the
 // asynchronous copy of the frame's |S| row there, into memory the plane overlaps.
+// The twiddle table of this variant is PAIRED (paired_twiddle_index): entry (k1 >> 1) * 32 + lane holds the twiddles
+// of k1 and k1 + 1 for this lane, so one 16 / 32-byte load fetches two of them (16 table loads instead of 31).
+template <typename C> struct alignas(2 * sizeof(C)) TwiddlePair { C a, b; };
+SSTTS_HD constexpr int paired_twiddle_index(int k1, int lane) { return (((k1 >> 1) * 32 + lane) << 1) | (k1 & 1); }
+
 template <typename T, bool INV, bool P1_DIT, bool P2_DIT, int ZLO, int ZHI, typename Mid>
 SSTTS_D void warp_fft1024_cx(T (&re)[32], T (&im)[32], typename cx_of<T>::type* xc,
                              const typename cx_of<T>::type* tw, int lane, Mid mid) {
   typedef typename cx_of<T>::type C;
   fft32<T, INV, P1_DIT, (P1_DIT ? ZLO : 0), (P1_DIT ? ZHI : 31)>(re, im);
+  const TwiddlePair<C>* tw2 = reinterpret_cast<const TwiddlePair<C>*>(tw);
 #pragma unroll
-  for (int k1 = 1; k1 < 32; ++k1) {
-    const int p = P1_DIT ? k1 : brev5(k1);
-    const C w = tw[k1 * 32 + lane];
-    const T vr = re[p], vi = im[p];
-    if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
-    else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
+  for (int kp = 0; kp < 32; kp += 2) {
+    const TwiddlePair<C> wp = tw2[(kp >> 1) * 32 + lane];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k1 = kp + h;
+      if (k1 == 0) continue;      // W^0 = 1
+      const int p = P1_DIT ? k1 : brev5(k1);
+      const C w = h ? wp.b : wp.a;
+      const T vr = re[p], vi = im[p];
+      if (!INV) { re[p] = vr * w.x - vi * w.y; im[p] = vr * w.y + vi * w.x; }
+      else      { re[p] = vr * w.x + vi * w.y; im[p] = vi * w.x - vr * w.y; }
+    }
   }
   __syncwarp();   // the plane may overlap data other lanes were still reading (the |S| row in the core)
 #pragma unroll

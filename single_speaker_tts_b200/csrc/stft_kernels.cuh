@@ -236,6 +236,12 @@ SSTTS_D void replace_magnitude(T xr, T xi, T s, T& yr, T& yi, T& m2) {
 #ifndef SSTTS_GL_FRAME_SHIFT
 #define SSTTS_GL_FRAME_SHIFT 1
 #endif
+// 1: the synthesis window is applied by the overlap-add gather (an FMA with the thread's <= 5 window values, which
+// only depend on its hop residue) instead of by the frame's warp before the store: no window loads and multiplies
+// on the output side of the transform.
+#ifndef SSTTS_GL_WINDOW_IN_GATHER
+#define SSTTS_GL_WINDOW_IN_GATHER 1
+#endif
 // 1: the float32 n_fft 2048 Griffin-Lim kernels exchange (re, im) pairs through a complex transpose plane
 // (warp_fft1024_cx) that overlaps the warp's |S| row buffer.
 #ifndef SSTTS_GL_COMPLEX_PLANE
@@ -620,7 +626,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
   sstts_mbar_t* s_bar = reinterpret_cast<sstts_mbar_t*>(smem + L.off_bar);
   int* s_cnt = reinterpret_cast<int*>(smem + L.off_bar + 8);    // warps that have consumed s_yin this round
 
-  for (int i = tid; i < (NATIVE ? 512 : 1024); i += NT) s_tw[i] = A.tab.tw1024[i];
+  // (the complex-plane transform reads its twiddles two at a time: paired table layout)
+  for (int i = tid; i < (NATIVE ? 512 : 1024); i += NT) s_tw[CXP ? paired_twiddle_index(i >> 5, i & 31) : i] = A.tab.tw1024[i];
   for (int i = tid; i < 512; i += NT) s_w2k[i] = A.tab.w2048[i];
   if (BULK && tid == 0) { sstts_mbar_init(s_bar, 1); *s_cnt = 0; }
   __syncthreads();
@@ -826,9 +833,12 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
           const int m = 32 * n1 + 2 * hl;
           const int i = m - lpad;
           if (m >= mlo && m < lpad + win + 1) {
-            const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
             C vv;
-            vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
+            if (SSTTS_GL_WINDOW_IN_GATHER) { vv.x = ro[n1]; vv.y = io[n1]; (void)i; }
+            else {
+              const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
+              vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
+            }
             *reinterpret_cast<C*>(oplane + (m - mlo)) = vv;        // m - mlo is even
           }
         }
@@ -944,9 +954,12 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         const bool inside = 64 * n1 >= mlo + 2 && 64 * n1 + 62 < lpad + win + 1;
         const bool outside = 64 * n1 + 62 < mlo || 64 * n1 >= lpad + win + 2;
         if (!outside && (inside || (m >= mlo_w && m < lp + win + 1))) {
-          const C w2 = *reinterpret_cast<const C*>(wout + i);    // zeros outside the window
           C vv;
-          vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
+          if (SSTTS_GL_WINDOW_IN_GATHER) { vv.x = ro[n1]; vv.y = io[n1]; (void)i; (void)wout; }
+          else {
+            const C w2 = *reinterpret_cast<const C*>(wout + i);  // zeros outside the window
+            vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
+          }
           *reinterpret_cast<C*>(plane + (m - mlo_w)) = vv;       // m - mlo_w is even
         }
       }
@@ -976,7 +989,10 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
             T acc = T(0);
             for (int j = MAX_OVERLAP - 1; j >= 0; --j) {      // ascending frame order f = q - j
               const int f = q - j, off = r + j * hop;
-              if (f >= 0 && f < FT && off < win) acc += s_planes[f * pe + off + slot_off(f)];
+              if (f >= 0 && f < FT && off < win) {
+                if (SSTTS_GL_WINDOW_IN_GATHER) acc = fma(s_planes[f * pe + off + slot_off(f)], s_win[off], acc);
+                else acc += s_planes[f * pe + off + slot_off(f)];
+              }
             }
             dst[s] = acc;
           }
@@ -986,6 +1002,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
         T acc[F + MAX_OVERLAP - 1];
 #pragma unroll
         for (int q = 0; q < F + MAX_OVERLAP - 1; ++q) acc[q] = T(0);
+        T wj[MAX_OVERLAP];      // the window at this residue's offsets inside a frame
+#pragma unroll
+        for (int j = 0; j < MAX_OVERLAP; ++j) wj[j] = (SSTTS_GL_WINDOW_IN_GATHER && r + j * hop < win) ? s_win[r + j * hop] : T(0);
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           if (f < FT) {
@@ -993,7 +1012,10 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
 #pragma unroll
             for (int j = 0; j < MAX_OVERLAP; ++j) {
               const int off = r + j * hop;
-              if (off < win) acc[f + j] += s_planes[f * pe + off + dl];
+              if (off < win) {
+                if (SSTTS_GL_WINDOW_IN_GATHER) acc[f + j] = fma(s_planes[f * pe + off + dl], wj[j], acc[f + j]);
+                else acc[f + j] += s_planes[f * pe + off + dl];
+              }
             }
           }
         }
