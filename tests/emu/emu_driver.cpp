@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "cpu_simt.h"
@@ -85,23 +86,25 @@ int emu_gl_run(int win, int hop, int n_utts, const long long* frame_off, const f
   const bool bulk = !NATIVE && sizeof(T) == 4 && stg && std::string(stg) == "bulk";
   const size_t smem = gl_step_smem_bytes<T>(W, win, hop, H.span_max, bulk, NATIVE);
   int grid = A.n_tiles < grid_cap ? A.n_tiles : grid_cap;
+  // one launch of the step kernel in the selected staging variant (the bulk variant exists for the 2048-point kernels)
+  auto step = [&](auto from_phase, auto want_mse) {
+    constexpr bool FP = decltype(from_phase)::value, MSE = decltype(want_mse)::value;
+    if constexpr (!NATIVE) {
+      if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, FP, MSE, true>(A); }); return; }
+    }
+    emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, FP, MSE>(A); });
+  };
   A.pin0 = nullptr; A.pin1 = nullptr; A.pout0 = buf[0]; A.pout1 = buf[1];
-  if constexpr (!NATIVE) { if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false, true>(A); }); } }
-  if (bulk) {}
-  else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, true, false>(A); });
+  step(std::true_type(), std::false_type());
   int cur = 0;
   for (int it = 0; it < n_iter; ++it) {
     A.pin0 = buf[2 * cur]; A.pin1 = buf[2 * cur + 1];
     A.pout0 = buf[2 * (cur ^ 1)]; A.pout1 = buf[2 * (cur ^ 1) + 1];
     if (it == n_iter - 1 && mse_frame) {
       A.mse_frame = mse_frame;
-      if constexpr (!NATIVE) { if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true, true>(A); }); } }
-      if (bulk) {}
-      else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, true>(A); });
+      step(std::false_type(), std::true_type());
     } else {
-      if constexpr (!NATIVE) { if (bulk) { emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false, true>(A); }); } }
-      if (bulk) {}
-      else emu::launch(dim3(grid), dim3(W * 32), smem, [&]() { gl_step_kernel<T, G, W, false, false>(A); });
+      step(std::false_type(), std::false_type());
     }
     cur ^= 1;
   }
