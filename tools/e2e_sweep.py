@@ -20,13 +20,13 @@ mag = fb.spec.abs().contiguous().cpu().numpy()
 off = np.concatenate([[0], np.cumsum(fb.frames)])
 mags = [mag[off[i]:off[i + 1]].T for i in range(256)]
 audio_s = sum(HOP * (t - 1) for t in fb.frames) / 22050
-for first, growth, head, cap in ((10000, 1, None, None), (2500, 2, None, 10000), (1500, 2, None, 12000), (3000, 1.6, None, 10000), (2500, 2, None, 20000), (4000, 2, None, 16000), (10000, 1, None, None)):
+for first, growth, head, cap in ((10000, 1, None, None), (10000, 1, 2500, None), (10000, 1, 4000, None), (10000, 1, 1500, None), (2500, 2, None, 10000), (8000, 1, 2500, None), (12000, 1, 3000, None), (10000, 1, None, None)):
     _runtime._GL_CHUNK_FRAMES, _runtime._GL_CHUNK_GROWTH, _runtime._GL_CHUNK_HEAD, _runtime._GL_CHUNK_CAP = first, growth, head, cap
     n_sub = len(_runtime._split_by_frames(list(fb.frames), first, growth, head=head, cap=cap))
-    for _ in range(4):
+    for _ in range(8):
         synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1)
     ts = []
-    for _ in range(6):
+    for _ in range(8):
         t0 = time.perf_counter()
         synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1)
         ts.append((time.perf_counter() - t0) * 1e3)

@@ -15,12 +15,14 @@ from single_speaker_tts_b200.audio import synthesis               # noqa: E402
 from single_speaker_tts_b200.synthetic import make_clips          # noqa: E402
 
 WIN, HOP, NFFT = 1102, 275, 2048
+if os.environ.get('E2E_HEAD'):      # size of the first sub-batch in frames (default: like the others)
+    _runtime._GL_CHUNK_HEAD = int(os.environ['E2E_HEAD'])
 clips = make_clips(256, seed=1, pool=16)
 fb = _runtime.stft_features_batch(clips, NFFT, HOP, WIN, want_spec=True, precision='f32', keep_on_device=True)
 mag = fb.spec.abs().contiguous().cpu().numpy()
 off = np.concatenate([[0], np.cumsum(fb.frames)])
 mags = [mag[off[i]:off[i + 1]].T for i in range(256)]
-for _ in range(4):
+for _ in range(8):
     synthesis.spectrograms_to_wavs(mags, WIN, HOP, NFFT, 50, seed=1)
 import single_speaker_tts_b200 as pkg
 mag_pin = pkg.pinned_empty(mag.shape); mag_pin[:] = mag
