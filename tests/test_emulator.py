@@ -283,16 +283,11 @@ def test_address_sanitizer_run_of_the_emulated_kernels(tmp_path):
     import os
     import shutil
     import subprocess
+    import __graft_entry__ as ge
     if os.environ.get('SSTTS_SKIP_ASAN') or shutil.which('g++') is None:
         pytest.skip('g++ / ASAN run disabled')
-    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu')
-    csrc = os.path.join(os.path.dirname(here), '..', 'single_speaker_tts_b200', 'csrc')
-    exe = str(tmp_path / 'asan_main')
-    build = subprocess.run(['g++', '-O1', '-g', '-std=c++20', '-fsanitize=address', '-pthread', '-Wno-unknown-pragmas',
-                            '-I', here, '-I', csrc, os.path.join(here, 'asan_main.cpp'), '-o', exe],
-                           capture_output=True, text=True)
-    if build.returncode != 0 and 'asan' in build.stderr.lower():
+    exe = ge.build_asan()          # cached in tests/emu/ like the emulator library (rebuilt when a source changes)
+    if exe is None:
         pytest.skip('no libasan in this toolchain')
-    assert build.returncode == 0, build.stderr[-2000:]
     run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and 'asan run ok' in run.stdout, (run.stdout + run.stderr)[-3000:]
