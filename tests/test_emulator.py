@@ -114,6 +114,25 @@ def test_griffin_lim_dynamic_geometry(emu):
     assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < 5e-7
 
 
+@pytest.mark.parametrize('win,hop', [(2048, 512), (2046, 512), (1500, 375)])
+def test_griffin_lim_frame_shift_boundaries(emu, win, hop):
+    """The iteration kernel transforms frames at odd span offsets one sample later in their zero-padded buffer
+    (aligned sample-pair loads).  win = n_fft leaves no room (the kernel must fall back to scalar loads),
+    win = n_fft - 2 is the last window length with room for the shift, 1500 / 375 alternates shifted and
+    unshifted frames; all must match the oracle in both precisions."""
+    rng = np.random.default_rng(21)
+    for T in (2, 9, 19):
+        x = speech_like_clip(hop * (T - 1) + 3, rng)
+        m = np.abs(lc.stft(x, NFFT, hop, win))
+        a = np.exp(2j * np.pi * np.random.RandomState(T).rand(*m.shape))
+        for prec, tol in ((1, 1e-6), (0, 1e-5)):
+            (w,), (mse,) = emu.griffin_lim([m], [a], 2, prec=prec, win=win, hop=hop, want_mse=True)
+            ref, rmse = ra.griffin_lim_v2(m, win, hop, NFFT, 2, angles=a, batched_fft=True)
+            assert w.shape == ref.shape and not np.isnan(w).any()
+            assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < tol, (win, hop, T, prec)
+            assert abs(mse - rmse) / rmse < 1e-5
+
+
 @pytest.mark.parametrize('n_fft,win,hop,native', [(1024, 1024, 256, '1'), (1024, 1024, 256, '0'), (1024, 800, 200, '1'),
                                                   (512, 400, 100, '1')])
 def test_griffin_lim_shorter_transforms(emu, monkeypatch, n_fft, win, hop, native):
