@@ -45,8 +45,9 @@ typedef enum sstts_precision {
 /* STFT geometry + mel filterbank.  Mirrors the arguments the reference threads through
  * audio/features.py:5-6,116 and audio/synthesis.py:43 (values: tacotron/params/model.py:13-33). */
 typedef struct sstts_stft_config {
-  int n_fft;         /* 2048, 1024 or 512.  Feature plans transform 1024 natively (512-point complex FFT on half a
-                        warp); Griffin-Lim plans and n_fft 512 run embedded in the 2048-point transform */
+  int n_fft;         /* 2048, 1024 or 512.  1024 is transformed natively (512-point complex FFT on half a warp, two
+                        frames per warp) by feature and Griffin-Lim plans; n_fft 512 runs embedded in the
+                        2048-point transform */
   int win_length;    /* <= n_fft, n_fft - win_length even; periodic Hann, zero-padded centred */
   int hop_length;    /* ceil(win_length / hop_length) <= 5 for Griffin-Lim */
   int sampling_rate; /* mel filterbank only */
