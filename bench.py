@@ -810,8 +810,9 @@ def run_ours(args):
     H = Harness()
     line = None
     # The sharded (strong-scaling) workloads run first: behind the 256-utterance workloads in the same process the
-    # corpus pass was 15-25 % slower at 2 and 4 GPUs (644 vs 492 ms per pass at 2 GPUs; allocator caches ruled out,
-    # cause not found), while this order leaves the other numbers unchanged.  BENCH_SHARDED_LAST=1: the old order.
+    # corpus pass was 15-25 % slower at 2 and 4 GPUs (644 vs 492 ms per pass at 2 GPUs; allocator caches ruled out;
+    # see DESIGN.md 7 for the unverified explanation: pinned buffers allocated before vs after the first collective),
+    # while this order leaves the other numbers unchanged.  BENCH_SHARDED_LAST=1: the old order.
     sharded_first = args.workload == 'all' and not args.no_sharded and os.environ.get('BENCH_SHARDED_LAST') != '1'
     if sharded_first:
         corpus = bench_corpus(H, args, args.clips or 13100)
