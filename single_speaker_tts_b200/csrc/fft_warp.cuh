@@ -378,6 +378,8 @@ SSTTS_D void warp_fft1024_cx(T (&re)[32], T (&im)[32], typename cx_of<T>::type* 
   typedef typename cx_of<T>::type C;
   fft32<T, INV, P1_DIT, (P1_DIT ? ZLO : 0), (P1_DIT ? ZHI : 31)>(re, im);
   const TwiddlePair<C>* tw2 = reinterpret_cast<const TwiddlePair<C>*>(tw);
+  SSTTS_CHECK_ALIGNED(tw2, sizeof(TwiddlePair<C>));
+  SSTTS_CHECK_ALIGNED(xc, sizeof(C));
 #pragma unroll
   for (int kp = 0; kp < 32; kp += 2) {
     const TwiddlePair<C> wp = tw2[(kp >> 1) * 32 + lane];

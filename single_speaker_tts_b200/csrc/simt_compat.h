@@ -14,6 +14,8 @@
 #define SSTTS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define SSTTS_HD __host__ __device__ __forceinline__
 #define SSTTS_D __device__ __forceinline__
+// alignment assertion of vector accesses: checked by the CPU emulator build only (tests/emu/cpu_simt.h)
+#define SSTTS_CHECK_ALIGNED(p, bytes) ((void)0)
 // 16-byte asynchronous global -> shared copy (LDGSTS); both addresses 16-byte aligned.
 __device__ __forceinline__ void sstts_cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -510,8 +510,9 @@ SSTTS_D void load_windowed_frame(T (&re)[32], T (&im)[32], const S* fin, const T
     C w2; w2.x = T(0); w2.y = T(0);
     S xa = S(0), xb = S(0);
     if (i + 1 >= 0 && i < win) {
+      SSTTS_CHECK_ALIGNED(s_win + i, sizeof(C));
       w2 = *reinterpret_cast<const C*>(s_win + i);       // window pair (zero outside the window) in one aligned load
-      if (PAIRED) { const S2 v = *reinterpret_cast<const S2*>(fin + m); xa = v.x; xb = v.y; }
+      if (PAIRED) { SSTTS_CHECK_ALIGNED(fin + m, sizeof(S2)); const S2 v = *reinterpret_cast<const S2*>(fin + m); xa = v.x; xb = v.y; }
       else { if (i >= 0) xa = fin[m]; if (i + 1 < win) xb = fin[m + 1]; }
     }
     re[brev5(n1)] = (i >= 0 && i < win) ? (T)xa * w2.x : T(0);
@@ -839,6 +840,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
               const C w2 = *reinterpret_cast<const C*>(s_win + i);   // zeros outside the window
               vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
             }
+            SSTTS_CHECK_ALIGNED(oplane + (m - mlo), sizeof(C));
             *reinterpret_cast<C*>(oplane + (m - mlo)) = vv;        // m - mlo is even
           }
         }
@@ -880,6 +882,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
           if (i_max + 1 < 0 || i_min >= win) {
             re[brev5(n1)] = T(0); im[brev5(n1)] = T(0);
           } else if (paired && i_min >= 0 && i_max + 1 < win) {
+            SSTTS_CHECK_ALIGNED(wtab + i, sizeof(C));
+            SSTTS_CHECK_ALIGNED(fin + m, sizeof(C));
             const C w2 = *reinterpret_cast<const C*>(wtab + i);
             const C x2 = *reinterpret_cast<const C*>(fin + m);
             re[brev5(n1)] = x2.x * w2.x;
@@ -888,8 +892,9 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
             C w2; w2.x = T(0); w2.y = T(0);
             C x2; x2.x = T(0); x2.y = T(0);
             if (i + 1 >= 0 && i < win) {
+              SSTTS_CHECK_ALIGNED(wtab + i, sizeof(C));
               w2 = *reinterpret_cast<const C*>(wtab + i);
-              if (paired) x2 = *reinterpret_cast<const C*>(fin + m);
+              if (paired) { SSTTS_CHECK_ALIGNED(fin + m, sizeof(C)); x2 = *reinterpret_cast<const C*>(fin + m); }
               else { x2.x = i >= 0 ? fin[m] : T(0); x2.y = i + 1 < win ? fin[m + 1] : T(0); }
             }
             re[brev5(n1)] = (i >= 0 && i < win) ? x2.x * w2.x : T(0);
@@ -960,6 +965,7 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? 2 : 1) gl_step_kernel
             const C w2 = *reinterpret_cast<const C*>(wout + i);  // zeros outside the window
             vv.x = ro[n1] * w2.x; vv.y = io[n1] * w2.y;
           }
+          SSTTS_CHECK_ALIGNED(plane + (m - mlo_w), sizeof(C));
           *reinterpret_cast<C*>(plane + (m - mlo_w)) = vv;       // m - mlo_w is even
         }
       }

@@ -16,6 +16,7 @@
 #include <math.h>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -34,6 +35,14 @@
 #define __shared__ static   /* blocks run one at a time, so function-static == block-shared */
 #define SSTTS_HD inline
 #define SSTTS_D inline
+// the hardware faults on a vector access that is not aligned to its size; x86 does not, so the emulator checks
+#define SSTTS_CHECK_ALIGNED(p, bytes)                                                                   \
+  do {                                                                                                  \
+    if (reinterpret_cast<uintptr_t>(p) % (bytes)) {                                                     \
+      std::fprintf(stderr, "misaligned %d-byte access at %s:%d\n", (int)(bytes), __FILE__, __LINE__);   \
+      std::abort();                                                                                     \
+    }                                                                                                   \
+  } while (0)
 
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
@@ -140,7 +149,11 @@ static inline V __shfl_down_sync(unsigned m, V v, int delta) {
   return __shfl_sync(m, v, src < 32 ? src : lane);
 }
 
-static inline void sstts_cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+static inline void sstts_cp_async16(void* smem_dst, const void* gmem_src) {
+  SSTTS_CHECK_ALIGNED(smem_dst, 16);
+  SSTTS_CHECK_ALIGNED(gmem_src, 16);
+  std::memcpy(smem_dst, gmem_src, 16);
+}
 static inline void sstts_cp_async4(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
 static inline void sstts_cp_async_wait_all() {}
 static inline float sstts_sqrt_approx(float x) { return sqrtf(x); }
