@@ -1387,6 +1387,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
               const bool valid = m >= 0 && m < A.n_mels;
               const float2* wp = reinterpret_cast<const float2*>(s_melp_w) + A.melp_woff[j] + lane;
               const float2* mg = reinterpret_cast<const float2*>(smf + (valid ? s_mel_k0[m] : 0));
+              SSTTS_CHECK_ALIGNED(mg, sizeof(float2));
+              SSTTS_CHECK_ALIGNED(wp, sizeof(float2));
               const int len = A.melp_len[j];
               float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll 4
@@ -1529,6 +1531,8 @@ __global__ void __launch_bounds__(W * 32, sizeof(T) == 4 ? SSTTS_FEAT_MINBLOCKS 
           // aligned and the pairs start at an even bin)
           const float2* wp = reinterpret_cast<const float2*>(s_melp_w) + A.melp_woff[j] + lane;
           const float2* mg = reinterpret_cast<const float2*>(s_mag + (valid ? s_mel_k0[m] : 0));
+          SSTTS_CHECK_ALIGNED(mg, sizeof(float2));
+          SSTTS_CHECK_ALIGNED(wp, sizeof(float2));
           const int len = A.melp_len[j];
           float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll 4
