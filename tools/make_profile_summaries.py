@@ -5,7 +5,11 @@
 writes profiles/TAG_ncu_summary.txt (tracked metrics + stall reasons per captured launch),
 profiles/TAG_*_sass_phases.txt (warp-instructions per frame by SASS run), profiles/TAG_traffic.json (per
 kernel: DRAM bytes per launch and the pipe utilisations bench.py quotes) and, with a launch list
-(`ncu --metrics gpu__time_duration.sum` of bench.py), profiles/TAG_bench_launch_shares.txt."""
+(`ncu --metrics gpu__time_duration.sum` of bench.py), profiles/TAG_bench_launch_shares.txt.
+
+A report with every kernel and --import-source exceeds gpurun's 64 MiB return limit, so round 2 captured the
+Griffin-Lim kernels (`-k regex:gl_step_kernel`, tag r2b) and the feature kernels (`-k regex:stft_feature_kernel`,
+tag r2c) separately and merged the two TAG_traffic.json files into profiles/r2_traffic.json."""
 import collections
 import csv
 import io
@@ -57,6 +61,7 @@ def first_index(pattern):
 # per-frame SASS phase tables: (file suffix, kernel substring, frames of that launch, title)
 for suffix, pat, frames, title in (
         ('gl', 'gl_step_kernel<float, StaticGeom<1102, 275, 2048>, 8, 0, 0, 0>', 112916, 'gl_step_kernel<float, model geometry> (iteration launch)'),
+        ('gl1024', 'gl_step_kernel<float, NativeGeom1024<1024, 256>, 8, 0, 0, 0>', 121282, 'gl_step_kernel<float, native n_fft 1024> (iteration launch)'),
         ('feat_f32', 'stft_feature_kernel<float, StaticGeom<1102, 275, 2048>, 8, 1>', 112916, 'stft_feature_kernel<float, model geometry, fused dB mode>'),
         ('feat_f64', 'stft_feature_kernel<double, StaticGeom<1102, 275, 2048>, 4, 1>', 112916, 'stft_feature_kernel<double, model geometry, fused dB mode>'),
         ('stats_f64', 'stft_feature_kernel<double, NativeGeom1024<1024, 256>, 4, 1>', 121282, 'stft_feature_kernel<double, native n_fft 1024, fused statistics mode>')):
